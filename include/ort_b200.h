@@ -1,0 +1,259 @@
+/* include/ort_b200.h -- C ABI of libort_b200.so, the B200 (sm_100a) replacement
+ * for the hot path of gyuhyun-lee/offline_raytracer: the per-pixel radiance loop
+ * `tiled_raytrace_bvh` (code/ray.cpp:1178-1466) and everything it calls.
+ *
+ * Plain pointers and sizes only -- no C++/torch/CUDA types -- so the library can
+ * be bound from the reference's C++ driver, from ctypes, or from any FFI.
+ * Scene inputs use the reference's own struct layouts (ort_scene.h).
+ *
+ * Every entry point cites the reference interface it replaces.  All functions
+ * return ORT_OK (0) or a negative error code and never abort; the message of
+ * the last error on the calling thread is available from ort_last_error().
+ * (The reference itself reports nothing: failures are assert() null-derefs,
+ * code/platform.h:16-20.)
+ *
+ * There is NO CPU fallback: every render / raycast entry point fails with
+ * ORT_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef ORT_B200_H
+#define ORT_B200_H
+
+#include "ort_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORT_OK              0
+#define ORT_ERR_ARG        -1   /* bad argument */
+#define ORT_ERR_CUDA       -2   /* CUDA runtime error / no device */
+#define ORT_ERR_IO         -3   /* file could not be read / written */
+#define ORT_ERR_PARSE      -4   /* malformed .scn / .ply / .obj */
+#define ORT_ERR_LIMIT      -5   /* a scene limit was exceeded */
+
+#define ORT_MISS_RANK 0xFFFFFFFFu
+
+/* which render kernel family runs the path */
+#define ORT_KERNEL_DEFAULT    0
+#define ORT_KERNEL_MEGAKERNEL 1   /* persistent threads, path regeneration, state in registers */
+#define ORT_KERNEL_WAVEFRONT  2   /* generate / extend / shade / accumulate kernels over path queues */
+
+/* fixed-point scale of the multi-chunk accumulation buffer (see OrtRenderParams.chunk_spp) */
+#define ORT_ACCUM_FRAC_BITS 24
+#define ORT_ACCUM_SAT_BITS  28   /* a chunk sum saturates at +-2^28 before conversion */
+
+typedef struct OrtScene OrtScene;         /* flattened, device-resident scene */
+typedef struct OrtHostScene OrtHostScene; /* host scene built by this library's own loaders */
+
+const char *ort_last_error(void);
+/* 0 when a usable CUDA device exists, else ORT_ERR_CUDA. */
+int ort_device_count(int *count);
+
+/* ------------------------------------------------------------------------
+ * Scene hand-off.
+ * Replaces: the (World*, BVHOctreeNode* top_most_node) arguments of
+ * tiled_raytrace_bvh (code/ray.cpp:1179) as assembled by main()
+ * (code/macos_main.mm:334-545).  All inputs are borrowed, read-only host
+ * pointers; nothing is retained after the call returns and nothing is freed.
+ * The octree is walked in the reference's breadth-first order to give every
+ * leaf record its tie-break RANK (the order in which raycast_bvh,
+ * code/ray.cpp:624-822, would test it with no culling); the records are then
+ * re-organised into a wide BVH with quantised child boxes and float4 triangles
+ * and uploaded to `device`.
+ * ---------------------------------------------------------------------- */
+typedef struct OrtSceneInfo
+{
+    uint32_t triangle_count;
+    uint32_t sphere_count, box_count, cylinder_count, csg_count;  /* csg records are inert (ray.cpp:718-767) and dropped */
+    uint32_t record_count;          /* = number of ranks */
+    uint32_t octree_node_count;     /* nodes reachable from top_most_node */
+    uint32_t octree_max_depth;
+    uint32_t material_count, light_count;
+    uint32_t bvh_node_count;        /* wide nodes of the flattened BVH */
+    uint32_t bvh_node_bytes;        /* bytes per wide node */
+    uint64_t device_bytes;          /* total device memory held by the handle */
+    float    root_min[3], root_max[3];
+} OrtSceneInfo;
+
+int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node,
+                     int device, OrtScene **scene_out);
+int ort_scene_destroy(OrtScene *scene);
+int ort_scene_info(const OrtScene *scene, OrtSceneInfo *info);
+
+/* ------------------------------------------------------------------------
+ * Render entry point, reference signature.
+ * Replaces: u64 tiled_raytrace_bvh(World*, Camera*, BVHOctreeNode*, v3 *output_buffer,
+ *   i32 output_width, i32 output_height, i32 tile_min_x, i32 tile_min_y,
+ *   i32 tile_one_past_max_x, i32 tile_one_past_max_y, RandomSeries *series,
+ *   u32 ray_per_pixel_count, f32 russian_roulette_value)   code/ray.cpp:1178-1183
+ * as called from thread_callback_tiled_raytrace (code/macos_main.mm:150-163).
+ *
+ * Same argument meaning and output layout: output_buffer is a HOST v3 array of
+ * output_width*output_height pixels, row 0 = bottom of the picture; only the
+ * tile's pixels are written, each with the mean radiance over
+ * ray_per_pixel_count samples.  *test_shape_count receives the number of
+ * primitive tests executed (the reference's return value has the same meaning
+ * for its own octree; the counts differ because the acceleration structure
+ * differs).
+ *
+ * RNG: the reference shares one sequential RandomSeries between all pixels of
+ * the tile, which cannot be parallelised.  Here the series' current state is
+ * the BASE SEED of independent per-pixel streams, stream(x, y) starting at
+ * ort_stream_seed(series->next_random, y*output_width + x, 0), each consumed in
+ * the reference's draw order; *series is then advanced by one
+ * xorshift step.  The reference reproduces any such seeding exactly by calling
+ * the unmodified tiled_raytrace_bvh on 1x1 tiles.
+ * ---------------------------------------------------------------------- */
+int ort_tiled_raytrace_bvh(OrtScene *scene, const OrtCamera *camera,
+                           ort_v3 *output_buffer, int32_t output_width, int32_t output_height,
+                           int32_t tile_min_x, int32_t tile_min_y,
+                           int32_t tile_one_past_max_x, int32_t tile_one_past_max_y,
+                           OrtRandomSeries *series, uint32_t ray_per_pixel_count,
+                           float russian_roulette_value, uint64_t *test_shape_count);
+
+/* ------------------------------------------------------------------------
+ * Render entry point, full form.
+ * The hot-loop literals of the reference are fields with the reference's
+ * values as defaults (ort_render_params_default).
+ * ---------------------------------------------------------------------- */
+typedef struct OrtRenderParams
+{
+    int32_t  output_width, output_height;
+    int32_t  tile_min_x, tile_min_y, tile_one_past_max_x, tile_one_past_max_y;
+    uint32_t ray_per_pixel_count;      /* total samples per pixel of the image */
+    float    russian_roulette_value;   /* 0.8 in the reference driver, macos_main.mm:656 */
+    uint32_t base_seed;
+    /* Sample streams.  The samples of one pixel are cut into chunks of chunk_spp
+     * samples; chunk c of pixel p is an independent xorshift stream seeded with
+     * ort_stream_seed(base_seed, p, c) and consumed sequentially.  chunk_spp = 0
+     * means one chunk per pixel (= ray_per_pixel_count): then the pixel is the
+     * float sum in sample order divided by spp, exactly the reference's
+     * accumulate (ray.cpp:1257,1364,1428).  With several chunks per pixel the
+     * chunk sums are combined in 64-bit fixed point (ORT_ACCUM_FRAC_BITS
+     * fractional bits, round-to-nearest-even, each chunk sum saturating at
+     * +-2^ORT_ACCUM_SAT_BITS), which is
+     * order-independent, so the image is bit-identical for any scheduling and
+     * any number of GPUs. */
+    uint32_t chunk_spp;
+    uint32_t chunk_begin, chunk_end;   /* sub-range of chunks rendered by this call; 0,0 = all */
+    uint32_t kernel;                   /* ORT_KERNEL_* */
+    float    roughness;                /* 0.01f   ray.cpp:1194 */
+    float    dont_get_too_close_epsilon; /* 0.0001f ray.cpp:1196 */
+    float    aperture_radius;          /* 0.1f    ray.cpp:1199 */
+    float    lens_z_offset;            /* 0.1f    ray.cpp:1234 */
+    float    focus_target[3];          /* (0,0,0.2) ray.cpp:1198 */
+} OrtRenderParams;
+
+typedef struct OrtRenderStats
+{
+    uint64_t samples;          /* pixel samples traced */
+    uint64_t rays;             /* extend calls: primary + bounce rays */
+    uint64_t node_visits;      /* wide-node visits       (counters build only, else 0) */
+    uint64_t box_tests;        /* child-box slab tests   (counters build only, else 0) */
+    uint64_t shape_tests;      /* primitive tests        (counters build only, else 0) */
+    float    device_ms;        /* CUDA-event time of the kernels of this call */
+    uint32_t kernel_launches;  /* kernels launched by this call */
+} OrtRenderStats;
+
+void ort_render_params_default(OrtRenderParams *params, int32_t width, int32_t height,
+                               uint32_t ray_per_pixel_count);
+
+/* host output (v3, row 0 = bottom); host<->device copies inside the call */
+int ort_render(OrtScene *scene, const OrtCamera *camera, const OrtRenderParams *params,
+               ort_v3 *output_buffer, OrtRenderStats *stats);
+
+/* Device-resident form for the multi-GPU path: adds the chunk sums of
+ * [chunk_begin, chunk_end) into `accum_device`, an int64[height*width*4]
+ * fixed-point buffer on the scene's device (zero it first with
+ * ort_accum_zero_device), on CUDA stream `stream` (a cudaStream_t passed as
+ * void*, NULL = default stream).  After the sum over ranks (ncclSum on int64 is
+ * exact), ort_accum_resolve_device writes float3 pixels = sum / spp. */
+int ort_render_accumulate_device(OrtScene *scene, const OrtCamera *camera,
+                                 const OrtRenderParams *params, void *accum_device,
+                                 void *stream, OrtRenderStats *stats);
+int ort_accum_zero_device(OrtScene *scene, void *accum_device, int32_t width, int32_t height, void *stream);
+int ort_accum_resolve_device(OrtScene *scene, const void *accum_device, int32_t width, int32_t height,
+                             uint32_t ray_per_pixel_count, void *rgb_device, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Ray-cast entry point, batched.
+ * Replaces: RaycastBVHResult raycast_top_most_node(BVHQueue*, BVHOctreeNode*,
+ *   u64 *test_shape_count, v3 ray_origin, v3 ray_dir)   code/ray.cpp:1165-1176
+ * (result struct code/ray.cpp:613-622) for n rays at once.  origins/dirs are
+ * xyz triples; dirs need not be unit (t is in units of |dir|).  Outputs (any
+ * may be NULL): hit_t (FLT_MAX on a miss, as ray.cpp:627), prim_rank (the
+ * winning record's rank, ORT_MISS_RANK on a miss -- the one addition to the
+ * reference's result), mat_index (0 on a miss), hit_normal (normalised xyz, as
+ * ray.cpp:817).  Closest hit with the reference's acceptance rule
+ * t >= 1e-6 && t < best (ray.cpp:653,670,686,708); exact-t ties go to the
+ * lowest rank, i.e. to the record the reference would have tested first.
+ * ---------------------------------------------------------------------- */
+int ort_raycast_batch(OrtScene *scene, uint64_t n, const float *origins, const float *dirs,
+                      float *hit_t, uint32_t *prim_rank, uint32_t *mat_index, float *hit_normal,
+                      OrtRenderStats *stats);
+/* same with device pointers on the scene's device; asynchronous on `stream` */
+int ort_raycast_batch_device(OrtScene *scene, uint64_t n, const float *origins, const float *dirs,
+                             float *hit_t, uint32_t *prim_rank, uint32_t *mat_index, float *hit_normal,
+                             void *stream);
+/* exhaustive closest hit over ALL records (no acceleration structure) with the
+ * same intersectors: the structure-free definition of the right answer
+ * (SURVEY.md 8c), used to validate the BVH at sizes the CPU oracle cannot reach. */
+int ort_raycast_brute_device(OrtScene *scene, uint64_t n, const float *origins, const float *dirs,
+                             float *hit_t, uint32_t *prim_rank, uint32_t *mat_index, void *stream);
+/* per-ray work counters of the traversal kernel on the given rays (device
+ * pointers): sums over the n rays of wide-node visits, child-box tests,
+ * primitive tests. */
+int ort_raycast_counters_device(OrtScene *scene, uint64_t n, const float *origins, const float *dirs,
+                                uint64_t *node_visits, uint64_t *box_tests, uint64_t *shape_tests);
+
+/* ------------------------------------------------------------------------
+ * Host side of the drop-in: this library's own re-implementation of the
+ * reference's loaders and scene assembly, producing the reference's structs.
+ * Replaces: parse_scene (code/parser.cpp:1184-1446), parse_ply_header/parse_ply
+ * (:384-570), pre_parse_obj/parse_obj (:687-982) and the scene assembly of
+ * main() (code/macos_main.mm:310-562: mesh bake, octree insertion with
+ * push_shape_inside_node code/ray.cpp:1799-1948, compaction, camera axes).
+ * with_csg != 0 inserts the reference's hard-coded (inert) CSG record
+ * (macos_main.mm:322-332) so that record ranks equal the reference's.
+ * ---------------------------------------------------------------------- */
+int ort_host_scene_load(const char *scn_path, const char *base_dir, int32_t width, int32_t height,
+                        int with_csg, OrtHostScene **out);
+int ort_host_scene_destroy(OrtHostScene *hs);
+const OrtWorld *ort_host_scene_world(const OrtHostScene *hs);
+const OrtCamera *ort_host_scene_camera(const OrtHostScene *hs);
+const OrtBVHOctreeNode *ort_host_scene_root(const OrtHostScene *hs);
+const OrtMesh *ort_host_scene_meshes(const OrtHostScene *hs, uint32_t *mesh_count);
+/* mesh loader alone; vertices (xyz floats) and indices are malloc'd, free with ort_free */
+int ort_load_mesh(const char *path, float **vertices, uint32_t *vertex_count,
+                  uint32_t **indices, uint32_t *index_count);
+/* the reference's number tokenizer (eat_numeric, code/parser.cpp:158-250), which is
+ * NOT strtof-equivalent; returns 1 for a float token, 0 for an integer token */
+int ort_parse_numeric(const char *text, uint32_t *value_bits);
+void ort_free(void *p);
+
+/* Radiance .hdr writer: flat (non-RLE) RGBE, header "+Y h +X w", buffer rows
+ * emitted h-1 -> 0.  Replaces v3_to_rgbe / write_hdr_header and the output loop
+ * of main() (code/macos_main.mm:242-287, 682-707). */
+int ort_write_hdr(const char *path, const ort_v3 *pixels, int32_t width, int32_t height);
+uint32_t ort_v3_to_rgbe(ort_v3 color);
+
+/* ------------------------------------------------------------------------
+ * Seed of the sample stream of (pixel, chunk).  Part of the boundary's
+ * contract: the CPU oracle uses the same function.  Never returns 0 (0 is the
+ * absorbing state of the reference's xorshift, code/random.h:5-16).
+ * ---------------------------------------------------------------------- */
+static inline uint32_t ort_stream_seed(uint32_t base, uint32_t pixel_index, uint32_t chunk)
+{
+    uint32_t h = base ^ (pixel_index * 0x9E3779B1u) ^ (chunk * 0x85EBCA77u);
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    if(h == 0) h = 0x6D2B79F5u;
+    return h;
+}
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ORT_B200_H */
