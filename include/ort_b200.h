@@ -242,6 +242,9 @@ uint32_t ort_v3_to_rgbe(ort_v3 color);
  * contract: the CPU oracle uses the same function.  Never returns 0 (0 is the
  * absorbing state of the reference's xorshift, code/random.h:5-16).
  * ---------------------------------------------------------------------- */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 static inline uint32_t ort_stream_seed(uint32_t base, uint32_t pixel_index, uint32_t chunk)
 {
     uint32_t h = base ^ (pixel_index * 0x9E3779B1u) ^ (chunk * 0x85EBCA77u);

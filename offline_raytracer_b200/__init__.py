@@ -1,0 +1,10 @@
+"""offline_raytracer_b200 -- B200 (sm_100a) hot path of gyuhyun-lee/offline_raytracer.
+
+The product is libort_b200.so (C ABI in include/ort_b200.h, sources in csrc/);
+this package is the thin host-side binding used by the tests and the benchmark.
+"""
+from .api import (  # noqa: F401
+    ORT_KERNEL_DEFAULT, ORT_KERNEL_MEGAKERNEL, ORT_KERNEL_WAVEFRONT, MISS_RANK,
+    OrtError, Camera, RenderParams, RenderStats, Scene, HostScene,
+    default_params, device_count, lib, load_mesh, parse_numeric, write_hdr, v3_to_rgbe,
+)

@@ -1,0 +1,315 @@
+"""ctypes binding of libort_b200.so -- the C ABI of include/ort_b200.h.
+
+Host-side mirror of the reference's render interface (code/ray.cpp):
+
+    reference                                        here
+    ---------------------------------------------    -----------------------------------------
+    main() scene assembly (macos_main.mm:310-562)    HostScene.load(scn_path, base_dir, w, h)
+    World* / BVHOctreeNode* hand-off                 Scene(world_ptr, root_ptr, device)
+    tiled_raytrace_bvh(...)        ray.cpp:1178      Scene.tiled_raytrace_bvh(...)
+    raycast_top_most_node(...)     ray.cpp:1165      Scene.raycast_batch(origins, dirs)
+
+There is no CPU fallback: if the CUDA library is missing or no device is usable
+every compute call raises OrtError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libort_b200.so")
+
+ORT_KERNEL_DEFAULT, ORT_KERNEL_MEGAKERNEL, ORT_KERNEL_WAVEFRONT = 0, 1, 2
+MISS_RANK = 0xFFFFFFFF
+ACCUM_FRAC_BITS = 24
+
+c_f, c_u32, c_i32, c_u64, vp = C.c_float, C.c_uint32, C.c_int32, C.c_uint64, C.c_void_p
+
+
+class OrtError(RuntimeError):
+    pass
+
+
+class V3(C.Structure):
+    _fields_ = [("x", c_f), ("y", c_f), ("z", c_f)]
+
+
+class Camera(C.Structure):
+    """OrtCamera == reference Camera (code/ray.h:42-49)"""
+    _fields_ = [("p", c_f * 3), ("x_axis", c_f * 3), ("y_axis", c_f * 3), ("z_axis", c_f * 3)]
+
+
+class RenderParams(C.Structure):
+    """OrtRenderParams (include/ort_b200.h)"""
+    _fields_ = [
+        ("output_width", c_i32), ("output_height", c_i32),
+        ("tile_min_x", c_i32), ("tile_min_y", c_i32),
+        ("tile_one_past_max_x", c_i32), ("tile_one_past_max_y", c_i32),
+        ("ray_per_pixel_count", c_u32), ("russian_roulette_value", c_f),
+        ("base_seed", c_u32), ("chunk_spp", c_u32),
+        ("chunk_begin", c_u32), ("chunk_end", c_u32), ("kernel", c_u32),
+        ("roughness", c_f), ("dont_get_too_close_epsilon", c_f),
+        ("aperture_radius", c_f), ("lens_z_offset", c_f),
+        ("focus_target", c_f * 3),
+    ]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("samples", c_u64), ("rays", c_u64), ("node_visits", c_u64), ("box_tests", c_u64),
+                ("shape_tests", c_u64), ("device_ms", c_f), ("kernel_launches", c_u32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("triangle_count", c_u32), ("sphere_count", c_u32), ("box_count", c_u32),
+                ("cylinder_count", c_u32), ("csg_count", c_u32), ("record_count", c_u32),
+                ("octree_node_count", c_u32), ("octree_max_depth", c_u32),
+                ("material_count", c_u32), ("light_count", c_u32),
+                ("bvh_node_count", c_u32), ("bvh_node_bytes", c_u32), ("device_bytes", c_u64),
+                ("root_min", c_f * 3), ("root_max", c_f * 3)]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_[:13]}
+        d["root_min"] = list(self.root_min); d["root_max"] = list(self.root_max)
+        return d
+
+
+_lib = None
+
+
+def lib(path=None):
+    """loads libort_b200.so (once); raises OrtError if it is not built"""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise OrtError("CUDA library %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                       "there is no CPU fallback" % p)
+    L = C.CDLL(p)
+    L.ort_last_error.restype = C.c_char_p
+    L.ort_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.ort_scene_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    L.ort_scene_destroy.argtypes = [vp]
+    L.ort_scene_info.argtypes = [vp, C.POINTER(SceneInfo)]
+    L.ort_render_params_default.argtypes = [C.POINTER(RenderParams), c_i32, c_i32, c_u32]
+    L.ort_render_params_default.restype = None
+    L.ort_render.argtypes = [vp, vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
+    L.ort_tiled_raytrace_bvh.argtypes = [vp, vp, vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                         C.POINTER(c_u32), c_u32, c_f, C.POINTER(c_u64)]
+    L.ort_render_accumulate_device.argtypes = [vp, vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
+    L.ort_accum_zero_device.argtypes = [vp, vp, c_i32, c_i32, vp]
+    L.ort_accum_resolve_device.argtypes = [vp, vp, c_i32, c_i32, c_u32, vp, vp]
+    L.ort_raycast_batch.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp, C.POINTER(RenderStats)]
+    L.ort_raycast_batch_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp, vp]
+    L.ort_raycast_brute_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp]
+    L.ort_raycast_counters_device.argtypes = [vp, c_u64, vp, vp, C.POINTER(c_u64), C.POINTER(c_u64), C.POINTER(c_u64)]
+    if hasattr(L, "ort_host_scene_load"):
+        L.ort_host_scene_load.argtypes = [C.c_char_p, C.c_char_p, c_i32, c_i32, C.c_int, C.POINTER(vp)]
+        L.ort_host_scene_destroy.argtypes = [vp]
+        for n in ("ort_host_scene_world", "ort_host_scene_camera", "ort_host_scene_root"):
+            getattr(L, n).argtypes = [vp]
+            getattr(L, n).restype = vp
+        L.ort_host_scene_meshes.argtypes = [vp, C.POINTER(c_u32)]
+        L.ort_host_scene_meshes.restype = vp
+        L.ort_load_mesh.argtypes = [C.c_char_p, C.POINTER(C.POINTER(c_f)), C.POINTER(c_u32),
+                                    C.POINTER(C.POINTER(c_u32)), C.POINTER(c_u32)]
+        L.ort_parse_numeric.argtypes = [C.c_char_p, C.POINTER(c_u32)]
+        L.ort_free.argtypes = [vp]
+        L.ort_write_hdr.argtypes = [C.c_char_p, vp, c_i32, c_i32]
+        L.ort_v3_to_rgbe.argtypes = [V3]
+        L.ort_v3_to_rgbe.restype = c_u32
+    if path is None:
+        _lib = L
+    return L
+
+
+def _check(rc, L=None):
+    if rc != 0:
+        L = L or lib()
+        raise OrtError("ort error %d: %s" % (rc, (L.ort_last_error() or b"").decode()))
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().ort_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def default_params(width, height, spp, rr=0.8, seed=1234567, chunk_spp=0, kernel=ORT_KERNEL_DEFAULT):
+    p = RenderParams()
+    lib().ort_render_params_default(C.byref(p), width, height, spp)
+    p.russian_roulette_value = rr
+    p.base_seed = seed
+    p.chunk_spp = chunk_spp
+    p.kernel = kernel
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def _as_ptr(x):
+    """accepts an int address, a ctypes pointer/void_p, or None"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return vp(x)
+    return C.cast(x, vp)
+
+
+class HostScene:
+    """Scene assembled on the host by this library's own loaders (the drop-in for
+    main(), code/macos_main.mm:310-562).  Holds the reference-layout World / Camera /
+    octree that Scene() consumes."""
+
+    def __init__(self, handle, width, height):
+        self.h, self.width, self.height = handle, width, height
+        L = lib()
+        self.world = L.ort_host_scene_world(handle)
+        self.camera = L.ort_host_scene_camera(handle)
+        self.root = L.ort_host_scene_root(handle)
+
+    @classmethod
+    def load(cls, scn_path, base_dir, width, height, with_csg=True):
+        L = lib()
+        if not base_dir.endswith("/"):
+            base_dir += "/"
+        h = vp(0)
+        _check(L.ort_host_scene_load(scn_path.encode(), base_dir.encode(), width, height, int(with_csg), C.byref(h)))
+        return cls(h, width, height)
+
+    def camera_array(self):
+        return np.ctypeslib.as_array(C.cast(self.camera, C.POINTER(c_f)), shape=(12,)).copy()
+
+    def close(self):
+        if self.h:
+            lib().ort_host_scene_destroy(self.h)
+            self.h = None
+
+
+class Scene:
+    """Device-resident flattened scene (OrtScene)."""
+
+    def __init__(self, world_ptr, root_ptr, device=0, library=None):
+        self.L = library or lib()
+        h = vp(0)
+        _check(self.L.ort_scene_create(_as_ptr(world_ptr), _as_ptr(root_ptr), device, C.byref(h)), self.L)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.L.ort_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        i = SceneInfo()
+        _check(self.L.ort_scene_info(self.h, C.byref(i)), self.L)
+        return i.as_dict()
+
+    # -- render ---------------------------------------------------------------
+    def render(self, camera_ptr, params, out=None):
+        """ort_render: returns (image[H,W,3] float32 with row 0 = bottom, stats dict)"""
+        W, H = params.output_width, params.output_height
+        if out is None:
+            out = np.zeros((H, W, 3), np.float32)
+        st = RenderStats()
+        _check(self.L.ort_render(self.h, _as_ptr(camera_ptr), C.byref(params), _ptr(out), C.byref(st)), self.L)
+        return out, st.as_dict()
+
+    def tiled_raytrace_bvh(self, camera_ptr, output_buffer, output_width, output_height,
+                           tile_min_x, tile_min_y, tile_one_past_max_x, tile_one_past_max_y,
+                           series, ray_per_pixel_count, russian_roulette_value):
+        """Same argument list as the reference's tiled_raytrace_bvh (code/ray.cpp:1178-1183) minus
+        the scene pointers.  `series` is a one-element uint32 array (RandomSeries.next_random),
+        advanced in place.  Returns the work counter."""
+        st = c_u32(int(series[0]))
+        cnt = c_u64(0)
+        _check(self.L.ort_tiled_raytrace_bvh(self.h, _as_ptr(camera_ptr), _ptr(output_buffer), output_width, output_height,
+                                             tile_min_x, tile_min_y, tile_one_past_max_x, tile_one_past_max_y,
+                                             C.byref(st), ray_per_pixel_count, c_f(russian_roulette_value), C.byref(cnt)),
+               self.L)
+        series[0] = st.value
+        return cnt.value
+
+    def render_accumulate_device(self, camera_ptr, params, accum_ptr, stream=None, want_stats=False):
+        st = RenderStats()
+        _check(self.L.ort_render_accumulate_device(self.h, _as_ptr(camera_ptr), C.byref(params), vp(accum_ptr),
+                                                   vp(stream) if stream else None,
+                                                   C.byref(st) if want_stats else None), self.L)
+        return st.as_dict() if want_stats else None
+
+    def accum_zero_device(self, accum_ptr, width, height, stream=None):
+        _check(self.L.ort_accum_zero_device(self.h, vp(accum_ptr), width, height, vp(stream) if stream else None), self.L)
+
+    def accum_resolve_device(self, accum_ptr, width, height, spp, rgb_ptr, stream=None):
+        _check(self.L.ort_accum_resolve_device(self.h, vp(accum_ptr), width, height, spp, vp(rgb_ptr),
+                                               vp(stream) if stream else None), self.L)
+
+    # -- ray cast ---------------------------------------------------------------
+    def raycast_batch(self, origins, dirs, want_normal=True):
+        """ort_raycast_batch on host arrays [n,3]; returns dict(t, rank, mat, normal, device_ms)"""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        t = np.zeros(n, np.float32); rank = np.zeros(n, np.uint32); mat = np.zeros(n, np.uint32)
+        nrm = np.zeros((n, 3), np.float32) if want_normal else None
+        st = RenderStats()
+        _check(self.L.ort_raycast_batch(self.h, n, _ptr(o), _ptr(d), _ptr(t), _ptr(rank), _ptr(mat), _ptr(nrm),
+                                        C.byref(st)), self.L)
+        return dict(t=t, rank=rank, mat=mat, normal=nrm, device_ms=st.device_ms)
+
+    def raycast_batch_device(self, n, origins_ptr, dirs_ptr, t_ptr=0, rank_ptr=0, mat_ptr=0, normal_ptr=0, stream=None):
+        _check(self.L.ort_raycast_batch_device(self.h, n, vp(origins_ptr), vp(dirs_ptr), vp(t_ptr) if t_ptr else None,
+                                               vp(rank_ptr) if rank_ptr else None, vp(mat_ptr) if mat_ptr else None,
+                                               vp(normal_ptr) if normal_ptr else None,
+                                               vp(stream) if stream else None), self.L)
+
+    def raycast_brute_device(self, n, origins_ptr, dirs_ptr, t_ptr=0, rank_ptr=0, mat_ptr=0, stream=None):
+        _check(self.L.ort_raycast_brute_device(self.h, n, vp(origins_ptr), vp(dirs_ptr), vp(t_ptr) if t_ptr else None,
+                                               vp(rank_ptr) if rank_ptr else None, vp(mat_ptr) if mat_ptr else None,
+                                               vp(stream) if stream else None), self.L)
+
+    def raycast_counters_device(self, n, origins_ptr, dirs_ptr):
+        a, b, c = c_u64(0), c_u64(0), c_u64(0)
+        _check(self.L.ort_raycast_counters_device(self.h, n, vp(origins_ptr), vp(dirs_ptr),
+                                                  C.byref(a), C.byref(b), C.byref(c)), self.L)
+        return dict(node_visits=a.value, box_tests=b.value, shape_tests=c.value)
+
+
+def load_mesh(path):
+    L = lib()
+    v = C.POINTER(c_f)(); i = C.POINTER(c_u32)()
+    nv = c_u32(0); ni = c_u32(0)
+    _check(L.ort_load_mesh(path.encode(), C.byref(v), C.byref(nv), C.byref(i), C.byref(ni)))
+    verts = np.ctypeslib.as_array(v, shape=(nv.value * 3,)).copy().reshape(-1, 3) if nv.value else np.zeros((0, 3), np.float32)
+    idx = np.ctypeslib.as_array(i, shape=(ni.value,)).copy() if ni.value else np.zeros(0, np.uint32)
+    L.ort_free(v); L.ort_free(i)
+    return verts, idx
+
+
+def parse_numeric(text):
+    bits = c_u32(0)
+    is_float = lib().ort_parse_numeric(text.encode(), C.byref(bits))
+    return int(is_float), bits.value
+
+
+def write_hdr(path, image):
+    img = np.ascontiguousarray(image, np.float32)
+    H, W = img.shape[:2]
+    _check(lib().ort_write_hdr(path.encode(), _ptr(img), W, H))
+
+
+def v3_to_rgbe(rgb):
+    return int(lib().ort_v3_to_rgbe(V3(float(rgb[0]), float(rgb[1]), float(rgb[2]))))

@@ -1,0 +1,290 @@
+// bvh.h -- flattened scene layout in HBM and the closest-hit traversal ("extend"),
+// shared by every kernel.  Replaces raycast_top_most_node / raycast_bvh
+// (code/ray.cpp:624-822, 1165-1176) and the pointer-based BVHOctreeNode octree
+// they walk (code/ray.h:115-133).
+//
+// LAYOUT (all 16-byte aligned, read with 128-bit loads):
+//   WideNode, 80 B = 5 x 16 B: an 8-wide BVH node whose child boxes are
+//   quantised to 8 bits per plane on a per-node power-of-two grid
+//   (origin p, biased exponents e), rounded OUTWARD so the quantised box always
+//   contains the child's float box (after Ylitie, Karras, Laine 2017,
+//   "Efficient incoherent ray traversal on GPUs through compressed wide BVHs").
+//     q0: p.x p.y p.z | ex ey ez imask            imask bit s = slot s is an inner node
+//     q1: child_base | prim_base | meta[0..3] | meta[4..7]
+//     q2: qlo_x[0..7] | qlo_y[0..7]
+//     q3: qlo_z[0..7] | qhi_x[0..7]
+//     q4: qhi_y[0..7] | qhi_z[0..7]
+//   meta[s]: 0 = empty; inner child: 0b001_11sss (low 5 bits = 24 + s);
+//            leaf child: (unary prim count 1/3/7) << 5 | offset of its first
+//            primitive from prim_base (<= 24 primitives per node, <= 3 per leaf).
+//   Inner children are stored contiguously from child_base in slot order.
+//   Slots are assigned so that slot s lies towards octant s of the node
+//   (bit0 = +x, bit1 = +y, bit2 = +z); a ray with sign-octant `oct` visits hit
+//   children in order of (s ^ (7 - oct)), highest first = front to back.
+//
+//   PrimRec, 48 B = 3 x 16 B: one record of the reference's leaf push buffers.
+//     q0: a.xyz | rank      q1: b.xyz | mat_index      q2: c.xyz | kind + (aux << 8)
+//     triangle: a,b,c = v0,v1,v2 UNTRANSFORMED -- the reference subtracts at test
+//               time (ray.cpp:87-92) and bit-exact t requires the same operands;
+//     sphere: a = center, b.x = r;   box: a = min, b = max;
+//     cylinder: aux indexes CylinderAux (base, rotation rows, |axis|, r).
+//   `rank` is the record's position in the order the reference's raycast_bvh
+//   would test records with no culling; exact-t ties go to the lowest rank,
+//   which reproduces "first tested wins" (strict `<` at ray.cpp:653-708).
+//
+// The traversal is closest-hit over the primitives with the reference's own
+// intersectors (core_math.h, namespace exact); the result is therefore the
+// argmin over ALL records of (t, rank) -- independent of the acceleration
+// structure -- provided the node boxes are conservative.  They are: every
+// primitive box is padded before quantisation (bvh_build.cpp) by more than the
+// rounding of the slab arithmetic below, and culling is inclusive (tmin <= tmax).
+#pragma once
+
+#include <string.h>
+
+#include "core_math.h"
+
+namespace ort {
+
+struct alignas(16) q4 { float x, y, z, w; };
+
+struct alignas(16) WideNode
+{
+    float px, py, pz;
+    uint8_t ex, ey, ez, imask;
+    uint32_t child_base, prim_base;
+    uint8_t meta[8];
+    uint8_t qlo_x[8], qlo_y[8];
+    uint8_t qlo_z[8], qhi_x[8];
+    uint8_t qhi_y[8], qhi_z[8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode is 5 x 16 B");
+
+struct alignas(16) PrimRec
+{
+    float ax, ay, az; uint32_t rank;
+    float bx, by, bz; uint32_t mat;
+    float cx, cy, cz; uint32_t kind;
+};
+static_assert(sizeof(PrimRec) == 48, "PrimRec is 3 x 16 B");
+
+enum { PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_AAB = 2, PRIM_CYLINDER = 3 };
+
+struct alignas(16) CylinderAux
+{
+    float base[3]; float axis_len;
+    float r0[3]; float radius;
+    float r1[3]; float pad0;
+    float r2[3]; float pad1;
+};
+static_assert(sizeof(CylinderAux) == 64, "CylinderAux is 4 x 16 B");
+
+struct SceneView
+{
+    const q4 *nodes;           // WideNode[node_count] viewed as q4[5*node_count]
+    const q4 *prims;           // PrimRec[prim_count] viewed as q4[3*prim_count]
+    const q4 *cyl;             // CylinderAux[] viewed as q4[4*n]
+    uint32_t node_count;
+    uint32_t prim_count;
+    // Two trees share the node array.  Nodes [0, main_root) hold the SPHERES and
+    // are traversed WITHOUT clipping to the best hit so far: a ray tangent to a
+    // sphere is reported by the reference at t = -b/(2a), half way to the sphere
+    // (code/ray.cpp:174-183), so a nearer hit must not cull the sphere's box.
+    // The main tree (everything else) starts at main_root and is clipped.
+    uint32_t main_root;
+};
+
+struct TraceCounters { uint32_t node_visits, box_tests, shape_tests; };
+
+struct TraceHit
+{
+    float t;          // FLT_MAX on a miss (ray.cpp:627)
+    uint32_t prim;    // index into prims, 0xFFFFFFFF on a miss
+    uint32_t rank;    // ORT_MISS_RANK on a miss
+};
+
+// ---- portable bit helpers --------------------------------------------------
+#if defined(__CUDA_ARCH__)
+ORT_HD q4 ldq(const q4 *p) { float4 v = __ldg(reinterpret_cast<const float4 *>(p)); q4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+ORT_HD uint32_t f2u(float f) { return __float_as_uint(f); }
+ORT_HD float u2f(uint32_t u) { return __uint_as_float(u); }
+ORT_HD uint32_t popc32(uint32_t v) { return (uint32_t)__popc(v); }
+ORT_HD uint32_t msb32(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
+ORT_HD uint32_t lsb32(uint32_t v) { return (uint32_t)__ffs((int)v) - 1u; }
+#else
+ORT_HD q4 ldq(const q4 *p) { return *p; }
+ORT_HD uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+ORT_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+ORT_HD uint32_t popc32(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
+ORT_HD uint32_t msb32(uint32_t v) { return 31u - (uint32_t)__builtin_clz(v); }
+ORT_HD uint32_t lsb32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
+#endif
+
+ORT_HD f3 q3(q4 v) { return mk3(v.x, v.y, v.z); }
+
+// exact intersection of one record (dispatch on kind); returns t (-1 = miss) and
+// the UNNORMALISED normal, as the reference's intersectors do.
+ORT_HD exact::Hit intersect_prim(const SceneView &s, uint32_t prim, f3 o, f3 d, uint32_t *rank, uint32_t *mat)
+{
+    const q4 *p = s.prims + 3u * prim;
+    q4 A = ldq(p), B = ldq(p + 1), C = ldq(p + 2);
+    *rank = f2u(A.w);
+    *mat = f2u(B.w);
+    uint32_t kind = f2u(C.w);
+    if((kind & 0xFFu) == PRIM_TRIANGLE) return exact::triangle(q3(A), q3(B), q3(C), o, d);
+    if((kind & 0xFFu) == PRIM_AAB) return exact::aab(q3(A), q3(B), o, d);
+    if((kind & 0xFFu) == PRIM_SPHERE) { int inner; return exact::sphere(q3(A), B.x, o, d, &inner); }
+    const q4 *c = s.cyl + 4u * (kind >> 8);
+    q4 c0 = ldq(c), c1 = ldq(c + 1), c2 = ldq(c + 2), c3 = ldq(c + 3);
+    exact::m3 rot; rot.r0 = q3(c1); rot.r1 = q3(c2); rot.r2 = q3(c3);
+    return exact::cylinder_pre(q3(c0), rot, c0.w, c1.w, o, d);
+}
+
+#ifndef ORT_STACK_SIZE
+#define ORT_STACK_SIZE 32
+#endif
+
+// select byte k (0..3) of w as float
+ORT_HD float byte_f(uint32_t w, uint32_t k) { return (float)((w >> (8u * k)) & 0xFFu); }
+
+// Closest hit.  COUNT adds work counters (the counters build of the same code,
+// SURVEY.md 8d).  o/d as in raycast_top_most_node; d need not be unit.
+template <bool COUNT>
+ORT_HD void trace(const SceneView &s, f3 o, f3 d, TraceHit *hit, TraceCounters *cnt)
+{
+    float best_t = FLT_MAX;
+    uint32_t best_prim = 0xFFFFFFFFu, best_rank = 0xFFFFFFFFu;
+
+    // reciprocal direction for the (conservative) slab tests; exact zeros and
+    // denormal-small components are clamped so that 0 * inf never appears
+    const float tiny = 1e-20f;
+    float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : (f2u(d.x) >> 31 ? -tiny : tiny));
+    float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : (f2u(d.y) >> 31 ? -tiny : tiny));
+    float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : (f2u(d.z) >> 31 ? -tiny : tiny));
+    const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
+    const uint32_t octinv = 7u - ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
+
+    uint32_t stack_x[ORT_STACK_SIZE], stack_y[ORT_STACK_SIZE];
+    int sp = 0;
+
+    // node group: a root as the single hit child of a virtual parent (imask 0 => relative index 0)
+    uint32_t ng_x = s.main_root, ng_y = 0x80000000u;
+    if(s.main_root != 0u) { stack_x[0] = 0u; stack_y[0] = 0x80000000u; sp = 1; }   // sphere tree, visited last
+
+    for(;;)
+    {
+        uint32_t tg_x = 0u, tg_y = 0u;        // primitive group
+        if(ng_y & 0xFF000000u)
+        {
+            uint32_t bit = msb32(ng_y);
+            uint32_t hits_imask = ng_y;
+            ng_y &= ~(1u << bit);
+            if(ng_y & 0xFF000000u)
+            {
+                if(sp < ORT_STACK_SIZE) { stack_x[sp] = ng_x; stack_y[sp] = ng_y; ++sp; }
+            }
+            uint32_t slot = (bit - 24u) ^ octinv;
+            uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+            const uint32_t node_index = ng_x + rel;
+            const float t_clip = (node_index >= s.main_root) ? best_t : FLT_MAX;
+            const q4 *np = s.nodes + 5u * node_index;
+            q4 n0 = ldq(np), n1 = ldq(np + 1), n2 = ldq(np + 2), n3 = ldq(np + 3), n4 = ldq(np + 4);
+            if(COUNT) cnt->node_visits++;
+
+            uint32_t e_imask = f2u(n0.w);
+            float ax = u2f((e_imask & 0xFFu) << 23) * idx;
+            float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * idy;
+            float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * idz;
+            float bx = (n0.x - o.x) * idx;
+            float by = (n0.y - o.y) * idy;
+            float bz = (n0.z - o.z) * idz;
+
+            ng_x = f2u(n1.x);
+            tg_x = f2u(n1.y);
+            uint32_t hitmask = 0u;
+#pragma unroll
+            for(int half = 0; half < 2; ++half)
+            {
+                uint32_t meta4 = half ? f2u(n1.w) : f2u(n1.z);
+                uint32_t lox = half ? f2u(n2.y) : f2u(n2.x);
+                uint32_t loy = half ? f2u(n2.w) : f2u(n2.z);
+                uint32_t loz = half ? f2u(n3.y) : f2u(n3.x);
+                uint32_t hix = half ? f2u(n3.w) : f2u(n3.z);
+                uint32_t hiy = half ? f2u(n4.y) : f2u(n4.x);
+                uint32_t hiz = half ? f2u(n4.w) : f2u(n4.z);
+                uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+                uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+                uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+#pragma unroll
+                for(uint32_t k = 0; k < 4; ++k)
+                {
+                    uint32_t meta = (meta4 >> (8u * k)) & 0xFFu;
+                    float t0x = fmaf(byte_f(nearx, k), ax, bx);
+                    float t0y = fmaf(byte_f(neary, k), ay, by);
+                    float t0z = fmaf(byte_f(nearz, k), az, bz);
+                    float t1x = fmaf(byte_f(farx, k), ax, bx);
+                    float t1y = fmaf(byte_f(fary, k), ay, by);
+                    float t1z = fmaf(byte_f(farz, k), az, bz);
+                    float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                    float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
+                    if(COUNT) { if(meta) cnt->box_tests++; }
+                    if(tmin <= tmax)
+                    {
+                        uint32_t child_bits = meta >> 5;
+                        uint32_t bit_index = meta & 31u;
+                        if(bit_index >= 24u) bit_index ^= octinv;
+                        hitmask |= child_bits << bit_index;
+                    }
+                }
+            }
+            ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);
+            tg_y = hitmask & 0x00FFFFFFu;
+        }
+        else
+        {
+            tg_x = ng_x; tg_y = ng_y;
+            ng_x = 0u; ng_y = 0u;
+        }
+
+        while(tg_y)
+        {
+            uint32_t bit = lsb32(tg_y);
+            tg_y &= tg_y - 1u;
+            uint32_t prim = tg_x + bit, rank, mat;
+            exact::Hit h = intersect_prim(s, prim, o, d, &rank, &mat);
+            (void)mat;
+            if(COUNT) cnt->shape_tests++;
+            // ray.cpp:653,670,686,708: t >= 1e-6 && t < best; exact ties -> lowest rank
+            if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < best_t || (h.t == best_t && rank < best_rank)))
+            {
+                best_t = h.t; best_prim = prim; best_rank = rank;
+            }
+        }
+
+        if(!(ng_y & 0xFF000000u))
+        {
+            if(sp == 0) break;
+            --sp;
+            ng_x = stack_x[sp]; ng_y = stack_y[sp];
+        }
+    }
+    hit->t = best_t; hit->prim = best_prim; hit->rank = best_rank;
+}
+
+// Re-evaluates the winning record to obtain the material and the normalised
+// normal (ray.cpp:817).  Same intersector, same operands => same bits as the
+// value the reference keeps from its own (single) evaluation.
+ORT_HD void finish_hit(const SceneView &s, const TraceHit &hit, f3 o, f3 d, uint32_t *mat, f3 *normal)
+{
+    if(hit.prim == 0xFFFFFFFFu)
+    {
+        *mat = 0u;
+        *normal = mk3(0.0f, 0.0f, 0.0f);
+        return;
+    }
+    uint32_t rank;
+    exact::Hit h = intersect_prim(s, hit.prim, o, d, &rank, mat);
+    *normal = normalize(h.n);
+}
+
+} // namespace ort

@@ -1,0 +1,508 @@
+// ort_b200.cu -- the extern "C" boundary (include/ort_b200.h) over the sm_100a
+// kernels: scene upload, render entry points, batched ray cast.
+// There is no CPU path in this file: without a CUDA device every entry point
+// that computes returns ORT_ERR_CUDA.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "scene_flatten.h"
+
+using namespace ort;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if(e__ != cudaSuccess)                                                             \
+            return fail(ORT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while(0)
+
+} // namespace
+
+struct OrtScene
+{
+    int device;
+    OrtSceneInfo info;
+    uint32_t main_root;
+    // device arrays (layout: bvh.h, scene_flatten.h)
+    q4 *d_nodes, *d_prims, *d_cyl, *d_materials;
+    uint8_t *d_light_is_sphere;
+    uint32_t node_count, prim_count, light_count;
+    // scratch owned by the handle
+    unsigned long long *d_stats;        // STAT_COUNT counters
+    long long *d_accum; size_t accum_pixels;
+    float *d_rgb; size_t rgb_pixels;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int sm_count;
+    int mega_blocks_per_sm, mega_blocks_per_sm_count;
+
+    SceneView view() const
+    {
+        SceneView v;
+        v.nodes = d_nodes; v.prims = d_prims; v.cyl = d_cyl;
+        v.node_count = node_count; v.prim_count = prim_count; v.main_root = main_root;
+        return v;
+    }
+};
+
+namespace {
+
+template <typename T>
+int upload(T **dst, const void *src, size_t bytes, uint64_t *total)
+{
+    *dst = 0;
+    size_t alloc = bytes ? bytes : 16;
+    CUDA_TRY(cudaMalloc((void **)dst, alloc));
+    if(bytes) CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    *total += alloc;
+    return ORT_OK;
+}
+
+int ensure_accum(OrtScene *s, size_t pixels)
+{
+    if(s->accum_pixels >= pixels) return ORT_OK;
+    if(s->d_accum) cudaFree(s->d_accum);
+    s->d_accum = 0; s->accum_pixels = 0;
+    CUDA_TRY(cudaMalloc((void **)&s->d_accum, pixels * 4 * sizeof(long long)));
+    s->accum_pixels = pixels;
+    return ORT_OK;
+}
+
+int ensure_rgb(OrtScene *s, size_t pixels)
+{
+    if(s->rgb_pixels >= pixels) return ORT_OK;
+    if(s->d_rgb) cudaFree(s->d_rgb);
+    s->d_rgb = 0; s->rgb_pixels = 0;
+    CUDA_TRY(cudaMalloc((void **)&s->d_rgb, pixels * 3 * sizeof(float)));
+    s->rgb_pixels = pixels;
+    return ORT_OK;
+}
+
+int check_params(const OrtRenderParams *P)
+{
+    if(!P) return fail(ORT_ERR_ARG, "null params");
+    if(P->output_width <= 0 || P->output_height <= 0) return fail(ORT_ERR_ARG, "output size must be positive");
+    if((int64_t)P->output_width * P->output_height > 0x7FFFFFFFll) return fail(ORT_ERR_ARG, "image too large");
+    if(P->tile_min_x < 0 || P->tile_min_y < 0 || P->tile_one_past_max_x > P->output_width ||
+       P->tile_one_past_max_y > P->output_height || P->tile_min_x > P->tile_one_past_max_x ||
+       P->tile_min_y > P->tile_one_past_max_y)
+        return fail(ORT_ERR_ARG, "tile rect outside the image");
+    if(P->ray_per_pixel_count == 0) return fail(ORT_ERR_ARG, "ray_per_pixel_count must be > 0");
+    if(P->kernel > ORT_KERNEL_WAVEFRONT) return fail(ORT_ERR_ARG, "unknown kernel id");
+    return ORT_OK;
+}
+
+struct ChunkPlan { uint32_t chunk_spp, n_chunks, begin, count; };
+
+ChunkPlan plan_chunks(const OrtRenderParams *P)
+{
+    ChunkPlan c;
+    uint32_t spp = P->ray_per_pixel_count;
+    c.chunk_spp = P->chunk_spp ? P->chunk_spp : spp;
+    if(c.chunk_spp > spp) c.chunk_spp = spp;
+    c.n_chunks = (spp + c.chunk_spp - 1) / c.chunk_spp;
+    uint32_t b = P->chunk_begin, e = P->chunk_end;
+    if(b == 0 && e == 0) e = c.n_chunks;
+    if(e > c.n_chunks) e = c.n_chunks;
+    if(b > e) b = e;
+    c.begin = b; c.count = e - b;
+    return c;
+}
+
+PathConsts make_consts(const OrtScene *s, const OrtCamera *cam, const OrtRenderParams *P)
+{
+    PathConsts c;
+    c.cam_p = mk3(cam->p.x, cam->p.y, cam->p.z);
+    c.cam_x = mk3(cam->x_axis.x, cam->x_axis.y, cam->x_axis.z);
+    c.cam_y = mk3(cam->y_axis.x, cam->y_axis.y, cam->y_axis.z);
+    c.cam_z = mk3(cam->z_axis.x, cam->z_axis.y, cam->z_axis.z);
+    // ray.cpp:1198, evaluated once on the host with the same IEEE operations
+    c.focal_length = length(c.cam_p - mk3(P->focus_target[0], P->focus_target[1], P->focus_target[2]));
+    c.aperture_radius = P->aperture_radius;
+    c.lens_z_offset = P->lens_z_offset;
+    c.roughness = P->roughness;
+    c.eps = P->dont_get_too_close_epsilon;
+    c.rr = P->russian_roulette_value;
+    c.width = P->output_width; c.height = P->output_height;
+    c.light_count = s->light_count;
+    c.light_is_sphere = s->d_light_is_sphere;
+    c.materials = s->d_materials;
+    return c;
+}
+
+// launches the render kernels for the chunk range of P into accum (fixed point)
+// or rgb (single-chunk float mode); exactly one of the two is non-null
+int launch_render(OrtScene *s, const OrtCamera *cam, const OrtRenderParams *P, const ChunkPlan &cp,
+                  long long *accum, float *rgb, cudaStream_t stream, uint32_t *launches)
+{
+    int tw = P->tile_one_past_max_x - P->tile_min_x, th = P->tile_one_past_max_y - P->tile_min_y;
+    if(tw <= 0 || th <= 0 || cp.count == 0) return ORT_OK;
+    if(P->kernel == ORT_KERNEL_WAVEFRONT) return fail(ORT_ERR_ARG, "wavefront kernels are not built into this library yet");
+
+    RenderArgs a;
+    a.scene = s->view();
+    a.pc = make_consts(s, cam, P);
+    a.tile_min_x = P->tile_min_x; a.tile_min_y = P->tile_min_y; a.tile_w = tw; a.tile_h = th;
+    a.blocks_x = (uint32_t)(tw + 7) / 8u; a.blocks_y = (uint32_t)(th + 3) / 4u;
+    a.spp = P->ray_per_pixel_count; a.chunk_spp = cp.chunk_spp; a.n_chunks = cp.n_chunks;
+    a.chunk_begin = cp.begin; a.chunk_count = cp.count;
+    a.base_seed = P->base_seed;
+    a.total_items = (unsigned long long)a.blocks_x * a.blocks_y * 32ull * cp.count;
+    a.work_counter = s->d_stats + STAT_WORK_COUNTER;
+    a.stats = s->d_stats;
+    a.accum = accum; a.rgb = rgb;
+
+    CUDA_TRY(cudaMemsetAsync(s->d_stats + STAT_WORK_COUNTER, 0, sizeof(unsigned long long), stream));
+    if(s->mega_blocks_per_sm == 0)
+    {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_mega<false>, 128, 0));
+        s->mega_blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    unsigned long long want = (a.total_items + 127ull) / 128ull;
+    unsigned long long grid = (unsigned long long)s->sm_count * s->mega_blocks_per_sm;
+    if(grid > want) grid = want;
+    if(grid == 0) grid = 1;
+#ifdef ORT_COUNTERS
+    k_render_mega<true><<<(unsigned)grid, 128, 0, stream>>>(a);
+#else
+    k_render_mega<false><<<(unsigned)grid, 128, 0, stream>>>(a);
+#endif
+    CUDA_TRY(cudaGetLastError());
+    *launches += 1;
+    return ORT_OK;
+}
+
+int read_stats(OrtScene *s, cudaStream_t stream, OrtRenderStats *stats, float ms, uint32_t launches)
+{
+    if(!stats) return ORT_OK;
+    unsigned long long h[STAT_COUNT];
+    CUDA_TRY(cudaMemcpyAsync(h, s->d_stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    stats->samples = h[STAT_SAMPLES]; stats->rays = h[STAT_RAYS];
+    stats->node_visits = h[STAT_NODE_VISITS]; stats->box_tests = h[STAT_BOX_TESTS]; stats->shape_tests = h[STAT_SHAPE_TESTS];
+    stats->device_ms = ms; stats->kernel_launches = launches;
+    return ORT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ort_last_error(void) { return g_last_error.c_str(); }
+void ort_set_last_error_(const char *msg) { g_last_error = msg ? msg : ""; }   // used by host_scene.cpp
+
+int ort_device_count(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if(count) *count = (e == cudaSuccess) ? n : 0;
+    if(e != cudaSuccess || n == 0) return fail(ORT_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return ORT_OK;
+}
+
+int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, OrtScene **scene_out)
+{
+    if(!scene_out) return fail(ORT_ERR_ARG, "scene_out is null");
+    *scene_out = 0;
+    int n = 0;
+    if(ort_device_count(&n) != ORT_OK) return ORT_ERR_CUDA;
+    if(device < 0 || device >= n) return fail(ORT_ERR_ARG, "device ordinal out of range");
+
+    FlatScene flat;
+    std::string err;
+    BuildOptions opt;
+    if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
+    if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
+    int rc = flatten_scene(world, top_most_node, opt, &flat, &err);
+    if(rc != ORT_OK) return fail(rc, err);
+
+    CUDA_TRY(cudaSetDevice(device));
+    OrtScene *s = new OrtScene();
+    memset(s, 0, sizeof(*s));
+    s->device = device;
+    s->info = flat.info;
+    s->main_root = flat.main_root;
+    s->node_count = (uint32_t)flat.nodes.size();
+    s->prim_count = (uint32_t)flat.prims.size();
+    s->light_count = (uint32_t)flat.light_is_sphere.size();
+    uint64_t total = 0;
+    rc = upload(&s->d_nodes, flat.nodes.data(), flat.nodes.size() * sizeof(WideNode), &total);
+    if(rc == ORT_OK) rc = upload(&s->d_prims, flat.prims.data(), flat.prims.size() * sizeof(PrimRec), &total);
+    if(rc == ORT_OK) rc = upload(&s->d_cyl, flat.cylinders.data(), flat.cylinders.size() * sizeof(CylinderAux), &total);
+    if(rc == ORT_OK) rc = upload(&s->d_materials, flat.materials.data(), flat.materials.size() * sizeof(DevMaterial), &total);
+    if(rc == ORT_OK) rc = upload(&s->d_light_is_sphere, flat.light_is_sphere.data(), flat.light_is_sphere.size(), &total);
+    if(rc == ORT_OK) rc = upload(&s->d_stats, (const void *)0, 0, &total);
+    if(rc != ORT_OK) { ort_scene_destroy(s); return rc; }
+    cudaFree(s->d_stats); s->d_stats = 0;
+    CUDA_TRY(cudaMalloc((void **)&s->d_stats, STAT_COUNT * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&s->ev0));
+    CUDA_TRY(cudaEventCreate(&s->ev1));
+    CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
+    s->info.device_bytes = total;
+    *scene_out = s;
+    return ORT_OK;
+}
+
+int ort_scene_destroy(OrtScene *s)
+{
+    if(!s) return ORT_OK;
+    cudaSetDevice(s->device);
+    if(s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_cyl); cudaFree(s->d_materials);
+    cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb);
+    if(s->ev0) cudaEventDestroy(s->ev0);
+    if(s->ev1) cudaEventDestroy(s->ev1);
+    if(s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return ORT_OK;
+}
+
+int ort_scene_info(const OrtScene *s, OrtSceneInfo *info)
+{
+    if(!s || !info) return fail(ORT_ERR_ARG, "null argument");
+    *info = s->info;
+    return ORT_OK;
+}
+
+void ort_render_params_default(OrtRenderParams *p, int32_t width, int32_t height, uint32_t ray_per_pixel_count)
+{
+    memset(p, 0, sizeof(*p));
+    p->output_width = width; p->output_height = height;
+    p->tile_one_past_max_x = width; p->tile_one_past_max_y = height;
+    p->ray_per_pixel_count = ray_per_pixel_count;
+    p->russian_roulette_value = 0.8f;          // macos_main.mm:656
+    p->base_seed = 1234567u;
+    p->kernel = ORT_KERNEL_DEFAULT;
+    p->roughness = 0.01f;                      // ray.cpp:1194
+    p->dont_get_too_close_epsilon = 0.0001f;   // ray.cpp:1196
+    p->aperture_radius = 0.1f;                 // ray.cpp:1199
+    p->lens_z_offset = 0.1f;                   // ray.cpp:1234
+    p->focus_target[0] = 0.0f; p->focus_target[1] = 0.0f; p->focus_target[2] = 0.2f;   // ray.cpp:1198
+}
+
+int ort_render(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, ort_v3 *output_buffer, OrtRenderStats *stats)
+{
+    if(!s || !camera || !output_buffer) return fail(ORT_ERR_ARG, "null argument");
+    int rc = check_params(P);
+    if(rc != ORT_OK) return rc;
+    CUDA_TRY(cudaSetDevice(s->device));
+    ChunkPlan cp = plan_chunks(P);
+    size_t pixels = (size_t)P->output_width * P->output_height;
+    int tw = P->tile_one_past_max_x - P->tile_min_x, th = P->tile_one_past_max_y - P->tile_min_y;
+    rc = ensure_rgb(s, pixels);
+    if(rc != ORT_OK) return rc;
+    const bool fixed = cp.n_chunks > 1;
+    if(fixed) { rc = ensure_accum(s, pixels); if(rc != ORT_OK) return rc; }
+    uint32_t launches = 0;
+    cudaStream_t st = s->stream;
+    CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaEventRecord(s->ev0, st));
+    if(fixed)
+    {
+        // only the tile's rows need clearing, but rows are contiguous: clear [min_y, max_y)
+        size_t off = (size_t)P->tile_min_y * P->output_width * 4;
+        size_t cnt = (size_t)th * P->output_width * 4;
+        if(cnt) CUDA_TRY(cudaMemsetAsync(s->d_accum + off, 0, cnt * sizeof(long long), st));
+    }
+    rc = launch_render(s, camera, P, cp, fixed ? s->d_accum : 0, fixed ? 0 : s->d_rgb, st, &launches);
+    if(rc != ORT_OK) return rc;
+    if(fixed && tw > 0 && th > 0)
+    {
+        int n = tw * th;
+        k_resolve_fixed<<<(n + 255) / 256, 256, 0, st>>>(s->d_accum, s->d_rgb, P->output_width, P->tile_min_x, P->tile_min_y,
+                                                          tw, th, P->ray_per_pixel_count);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(s->ev1, st));
+    if(tw > 0 && th > 0)
+    {
+        // device -> host, tile rows only (the reference writes only the tile's pixels, ray.cpp:1201-1436)
+        CUDA_TRY(cudaMemcpy2DAsync(output_buffer + (size_t)P->tile_min_y * P->output_width + P->tile_min_x,
+                                   (size_t)P->output_width * sizeof(ort_v3),
+                                   s->d_rgb + 3 * ((size_t)P->tile_min_y * P->output_width + P->tile_min_x),
+                                   (size_t)P->output_width * 3 * sizeof(float),
+                                   (size_t)tw * sizeof(ort_v3), (size_t)th, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    return read_stats(s, st, stats, ms, launches);
+}
+
+int ort_tiled_raytrace_bvh(OrtScene *scene, const OrtCamera *camera, ort_v3 *output_buffer,
+                           int32_t output_width, int32_t output_height,
+                           int32_t tile_min_x, int32_t tile_min_y, int32_t tile_one_past_max_x, int32_t tile_one_past_max_y,
+                           OrtRandomSeries *series, uint32_t ray_per_pixel_count, float russian_roulette_value,
+                           uint64_t *test_shape_count)
+{
+    if(!series) return fail(ORT_ERR_ARG, "series is null");
+    OrtRenderParams P;
+    ort_render_params_default(&P, output_width, output_height, ray_per_pixel_count);
+    P.tile_min_x = tile_min_x; P.tile_min_y = tile_min_y;
+    P.tile_one_past_max_x = tile_one_past_max_x; P.tile_one_past_max_y = tile_one_past_max_y;
+    P.russian_roulette_value = russian_roulette_value;
+    P.base_seed = series->next_random;
+    OrtRenderStats st; memset(&st, 0, sizeof(st));
+    int rc = ort_render(scene, camera, &P, output_buffer, &st);
+    if(rc != ORT_OK) return rc;
+    xor_shift_32(&series->next_random);
+    if(test_shape_count) *test_shape_count = st.shape_tests ? st.shape_tests : st.rays;
+    return ORT_OK;
+}
+
+int ort_accum_zero_device(OrtScene *s, void *accum_device, int32_t width, int32_t height, void *stream)
+{
+    if(!s || !accum_device || width <= 0 || height <= 0) return fail(ORT_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaMemsetAsync(accum_device, 0, (size_t)width * height * 4 * sizeof(long long), (cudaStream_t)stream));
+    return ORT_OK;
+}
+
+int ort_render_accumulate_device(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, void *accum_device,
+                                 void *stream, OrtRenderStats *stats)
+{
+    if(!s || !camera || !accum_device) return fail(ORT_ERR_ARG, "null argument");
+    int rc = check_params(P);
+    if(rc != ORT_OK) return rc;
+    CUDA_TRY(cudaSetDevice(s->device));
+    ChunkPlan cp = plan_chunks(P);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t launches = 0;
+    CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaEventRecord(s->ev0, st));
+    rc = launch_render(s, camera, P, cp, (long long *)accum_device, 0, st, &launches);
+    if(rc != ORT_OK) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev1, st));
+    if(stats)
+    {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        return read_stats(s, st, stats, ms, launches);
+    }
+    return ORT_OK;
+}
+
+int ort_accum_resolve_device(OrtScene *s, const void *accum_device, int32_t width, int32_t height,
+                             uint32_t ray_per_pixel_count, void *rgb_device, void *stream)
+{
+    if(!s || !accum_device || !rgb_device || width <= 0 || height <= 0 || ray_per_pixel_count == 0)
+        return fail(ORT_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int n = width * height;
+    k_resolve_fixed<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const long long *)accum_device, (float *)rgb_device,
+                                                                      width, 0, 0, width, height, ray_per_pixel_count);
+    CUDA_TRY(cudaGetLastError());
+    return ORT_OK;
+}
+
+int ort_raycast_batch_device(OrtScene *s, uint64_t n, const float *origins, const float *dirs,
+                             float *hit_t, uint32_t *prim_rank, uint32_t *mat_index, float *hit_normal, void *stream)
+{
+    if(!s || (n && (!origins || !dirs))) return fail(ORT_ERR_ARG, "null argument");
+    if(n == 0) return ORT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    unsigned long long want = (n + 127ull) / 128ull;
+    unsigned long long grid = (unsigned long long)s->sm_count * 8ull;
+    if(grid > want) grid = want;
+    k_raycast<false><<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(s->view(), n, origins, dirs, hit_t, prim_rank,
+                                                                        mat_index, hit_normal, s->d_stats);
+    CUDA_TRY(cudaGetLastError());
+    return ORT_OK;
+}
+
+int ort_raycast_brute_device(OrtScene *s, uint64_t n, const float *origins, const float *dirs,
+                             float *hit_t, uint32_t *prim_rank, uint32_t *mat_index, void *stream)
+{
+    if(!s || (n && (!origins || !dirs))) return fail(ORT_ERR_ARG, "null argument");
+    if(n == 0) return ORT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    unsigned long long grid = (n + 255ull) / 256ull;
+    k_raycast_brute<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(s->view(), n, origins, dirs, hit_t, prim_rank, mat_index);
+    CUDA_TRY(cudaGetLastError());
+    return ORT_OK;
+}
+
+int ort_raycast_counters_device(OrtScene *s, uint64_t n, const float *origins, const float *dirs,
+                                uint64_t *node_visits, uint64_t *box_tests, uint64_t *shape_tests)
+{
+    if(!s || (n && (!origins || !dirs))) return fail(ORT_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
+    if(n)
+    {
+        unsigned long long want = (n + 127ull) / 128ull;
+        unsigned long long grid = (unsigned long long)s->sm_count * 8ull;
+        if(grid > want) grid = want;
+        k_raycast<true><<<(unsigned)grid, 128, 0, st>>>(s->view(), n, origins, dirs, 0, 0, 0, 0, s->d_stats);
+        CUDA_TRY(cudaGetLastError());
+    }
+    unsigned long long h[STAT_COUNT];
+    CUDA_TRY(cudaMemcpyAsync(h, s->d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if(node_visits) *node_visits = h[STAT_NODE_VISITS];
+    if(box_tests) *box_tests = h[STAT_BOX_TESTS];
+    if(shape_tests) *shape_tests = h[STAT_SHAPE_TESTS];
+    return ORT_OK;
+}
+
+int ort_raycast_batch(OrtScene *s, uint64_t n, const float *origins, const float *dirs,
+                      float *hit_t, uint32_t *prim_rank, uint32_t *mat_index, float *hit_normal, OrtRenderStats *stats)
+{
+    if(!s || (n && (!origins || !dirs))) return fail(ORT_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if(stats) memset(stats, 0, sizeof(*stats));
+    if(n == 0) return ORT_OK;
+    cudaStream_t st = s->stream;
+    float *d_o = 0, *d_d = 0, *d_t = 0, *d_n = 0; uint32_t *d_r = 0, *d_m = 0;
+    int rc = ORT_OK;
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_n); cudaFree(d_r); cudaFree(d_m); };
+#define TRY_OR_CLEAN(expr) do { cudaError_t e__ = (expr); if(e__ != cudaSuccess) { cleanup(); return fail(ORT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while(0)
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_o, n * 3 * sizeof(float)));
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_d, n * 3 * sizeof(float)));
+    if(hit_t) TRY_OR_CLEAN(cudaMalloc((void **)&d_t, n * sizeof(float)));
+    if(prim_rank) TRY_OR_CLEAN(cudaMalloc((void **)&d_r, n * sizeof(uint32_t)));
+    if(mat_index) TRY_OR_CLEAN(cudaMalloc((void **)&d_m, n * sizeof(uint32_t)));
+    if(hit_normal) TRY_OR_CLEAN(cudaMalloc((void **)&d_n, n * 3 * sizeof(float)));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_o, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_d, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    TRY_OR_CLEAN(cudaEventRecord(s->ev0, st));
+    rc = ort_raycast_batch_device(s, n, d_o, d_d, d_t, d_r, d_m, d_n, st);
+    if(rc != ORT_OK) { cleanup(); return rc; }
+    TRY_OR_CLEAN(cudaEventRecord(s->ev1, st));
+    if(hit_t) TRY_OR_CLEAN(cudaMemcpyAsync(hit_t, d_t, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if(prim_rank) TRY_OR_CLEAN(cudaMemcpyAsync(prim_rank, d_r, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if(mat_index) TRY_OR_CLEAN(cudaMemcpyAsync(mat_index, d_m, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if(hit_normal) TRY_OR_CLEAN(cudaMemcpyAsync(hit_normal, d_n, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    TRY_OR_CLEAN(cudaStreamSynchronize(st));
+    if(stats)
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+        stats->rays = n; stats->device_ms = ms; stats->kernel_launches = 1;
+    }
+    cleanup();
+#undef TRY_OR_CLEAN
+    return ORT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,612 @@
+// scene_flatten.cpp -- octree -> ranked records -> 8-wide quantised BVH (host).
+//
+// Input is the reference's own scene hand-off (World + BVHOctreeNode root,
+// code/ray.h:76-133) exactly as main() leaves it (code/macos_main.mm:334-545).
+// Nothing of the octree's topology survives except the ORDER it imposes on the
+// leaf records -- the tie-break rank (bvh.h).  The acceleration structure that
+// is uploaded is rebuilt from the records: binned-SAH binary BVH, collapsed to
+// 8-wide, children placed in octant slots, boxes quantised outward.
+#include "scene_flatten.h"
+
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <deque>
+
+namespace ort {
+
+namespace {
+
+inline uint32_t payload_size(uint32_t type)
+{
+    switch(type)
+    {
+        case ORT_SHAPE_SPHERE:   return (uint32_t)sizeof(OrtSphere);
+        case ORT_SHAPE_AAB:      return (uint32_t)sizeof(OrtAAB);
+        case ORT_SHAPE_CYLINDER: return (uint32_t)sizeof(OrtCylinder);
+        case ORT_SHAPE_TRIANGLE: return (uint32_t)sizeof(OrtTriangle);
+        case ORT_SHAPE_CSG:      return (uint32_t)sizeof(OrtCSG);
+        default: return 0;
+    }
+}
+
+inline f3 v3(const ort_v3 &v) { return mk3(v.x, v.y, v.z); }
+
+inline bool node_is_live(const OrtBVHOctreeNode *c)   // the test at ray.cpp:788
+{
+    return (c->is_leaf && c->push_buffer.used) || c->first_child;
+}
+
+inline void grow(float *lo, float *hi, double x, double y, double z)
+{
+    if(x < lo[0]) lo[0] = (float)x; if(y < lo[1]) lo[1] = (float)y; if(z < lo[2]) lo[2] = (float)z;
+    if(x > hi[0]) hi[0] = (float)x; if(y > hi[1]) hi[1] = (float)y; if(z > hi[2]) hi[2] = (float)z;
+}
+
+// tight bounds of the region in which the reference's intersector for this
+// record can report a hit (before padding)
+void prim_bounds(HostPrim &p)
+{
+    for(int k = 0; k < 3; ++k) { p.lo[k] = FLT_MAX; p.hi[k] = -FLT_MAX; }
+    switch(p.kind)
+    {
+        case PRIM_TRIANGLE:
+            grow(p.lo, p.hi, p.a.x, p.a.y, p.a.z);
+            grow(p.lo, p.hi, p.b.x, p.b.y, p.b.z);
+            grow(p.lo, p.hi, p.c.x, p.c.y, p.c.z);
+            break;
+        case PRIM_SPHERE:
+        {
+            double r = fabs((double)p.radius);
+            grow(p.lo, p.hi, p.a.x - r, p.a.y - r, p.a.z - r);
+            grow(p.lo, p.hi, p.a.x + r, p.a.y + r, p.a.z + r);
+        } break;
+        case PRIM_AAB:
+            grow(p.lo, p.hi, p.a.x, p.a.y, p.a.z);
+            grow(p.lo, p.hi, p.b.x, p.b.y, p.b.z);
+            break;
+        case PRIM_CYLINDER:
+        {
+            // the intersector works in the frame R*(x - base) and accepts
+            // x^2+y^2 <= r^2, 0 <= z <= |axis| there (ray.cpp:294-324); R falls
+            // back to identity for axes parallel to Z (ray.cpp:13), whatever
+            // their sign -- bound exactly that region, not the "geometric" cylinder
+            exact::m3 rot = exact::rotation_matrix_along_z(p.b);
+            double len = length(p.b), r = fabs((double)p.radius);
+            for(int corner = 0; corner < 8; ++corner)
+            {
+                double lx = (corner & 1) ? r : -r, ly = (corner & 2) ? r : -r, lz = (corner & 4) ? len : 0.0;
+                // world = base + R^T * local
+                double wx = p.a.x + rot.r0.x * lx + rot.r1.x * ly + rot.r2.x * lz;
+                double wy = p.a.y + rot.r0.y * lx + rot.r1.y * ly + rot.r2.y * lz;
+                double wz = p.a.z + rot.r0.z * lx + rot.r1.z * ly + rot.r2.z * lz;
+                grow(p.lo, p.hi, wx, wy, wz);
+            }
+        } break;
+    }
+}
+
+} // namespace
+
+int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
+                    std::vector<HostPrim> *prims, FlatScene *out, std::string *err)
+{
+    if(!world || !root) { *err = "null world / top_most_node"; return ORT_ERR_ARG; }
+    memset(&out->info, 0, sizeof(out->info));
+
+    // full breadth-first walk: the order raycast_bvh pops nodes when no child is
+    // culled (queue push at ray.cpp:808, children 0..7, dead children skipped :788)
+    struct Item { const OrtBVHOctreeNode *node; uint32_t depth; };
+    std::deque<Item> queue;
+    queue.push_back(Item{ root, 0u });
+    uint32_t rank = 0;
+    while(!queue.empty())
+    {
+        Item it = queue.front(); queue.pop_front();
+        const OrtBVHOctreeNode *node = it.node;
+        out->info.octree_node_count++;
+        if(it.depth > out->info.octree_max_depth) out->info.octree_max_depth = it.depth;
+        const uint8_t *base = (const uint8_t *)node->push_buffer.base;
+        for(size_t consumed = 0; consumed < node->push_buffer.used; )
+        {
+            uint32_t type; memcpy(&type, base + consumed, 4);
+            uint32_t psize = payload_size(type);
+            if(psize == 0 || consumed + 4 + psize > node->push_buffer.used)
+            {
+                *err = "corrupt leaf push buffer (unknown shape type)";
+                return ORT_ERR_ARG;
+            }
+            const uint8_t *q = base + consumed + 4;
+            consumed += 4 + psize;
+            HostPrim p; memset(&p, 0, sizeof(p));
+            p.rank = rank++;
+            bool keep = true;
+            switch(type)
+            {
+                case ORT_SHAPE_SPHERE:
+                {
+                    OrtSphere s; memcpy(&s, q, sizeof(s));
+                    p.kind = PRIM_SPHERE; p.a = v3(s.center); p.radius = s.r; p.mat = s.mat_index;
+                    out->info.sphere_count++;
+                } break;
+                case ORT_SHAPE_AAB:
+                {
+                    OrtAAB s; memcpy(&s, q, sizeof(s));
+                    p.kind = PRIM_AAB; p.a = v3(s.min); p.b = v3(s.max); p.mat = s.mat_index;
+                    out->info.box_count++;
+                } break;
+                case ORT_SHAPE_CYLINDER:
+                {
+                    OrtCylinder s; memcpy(&s, q, sizeof(s));
+                    p.kind = PRIM_CYLINDER; p.a = v3(s.base); p.b = v3(s.axis); p.radius = s.r; p.mat = s.mat_index;
+                    out->info.cylinder_count++;
+                } break;
+                case ORT_SHAPE_TRIANGLE:
+                {
+                    OrtTriangle s; memcpy(&s, q, sizeof(s));
+                    if(!s.mesh || !s.mesh->vertices) { *err = "triangle record without mesh"; return ORT_ERR_ARG; }
+                    p.kind = PRIM_TRIANGLE;
+                    p.a = v3(s.mesh->vertices[s.i_0]);       // ray.cpp:702-704
+                    p.b = v3(s.mesh->vertices[s.i_1]);
+                    p.c = v3(s.mesh->vertices[s.i_2]);
+                    p.mat = s.mesh->mat_index;
+                    out->info.triangle_count++;
+                } break;
+                case ORT_SHAPE_CSG:
+                    keep = false;                           // inert record, ray.cpp:718-767
+                    out->info.csg_count++;
+                    break;
+                default:
+                    keep = false;
+                    break;
+            }
+            if(keep)
+            {
+                if(p.mat >= world->mat_count) { *err = "record with material index out of range"; return ORT_ERR_ARG; }
+                prim_bounds(p);
+                prims->push_back(p);
+            }
+        }
+        if(node->first_child)
+            for(uint32_t ci = 0; ci < 8; ++ci)
+            {
+                const OrtBVHOctreeNode *child = node->first_child + ci;
+                if(node_is_live(child)) queue.push_back(Item{ child, it.depth + 1 });
+            }
+    }
+    out->info.record_count = rank;
+    out->info.root_min[0] = root->aabb_min.x; out->info.root_min[1] = root->aabb_min.y; out->info.root_min[2] = root->aabb_min.z;
+    out->info.root_max[0] = root->aabb_max.x; out->info.root_max[1] = root->aabb_max.y; out->info.root_max[2] = root->aabb_max.z;
+
+    // materials (index 0 = "miss", parser.cpp:1187)
+    out->materials.resize(world->mat_count ? world->mat_count : 1);
+    memset(out->materials.data(), 0, out->materials.size() * sizeof(DevMaterial));
+    for(uint32_t i = 0; i < world->mat_count; ++i)
+    {
+        const OrtMaterial &m = world->materials[i];
+        DevMaterial &dm = out->materials[i];
+        dm.diffuse[0] = m.diffuse.x; dm.diffuse[1] = m.diffuse.y; dm.diffuse[2] = m.diffuse.z;
+        dm.specular[0] = m.specular.x; dm.specular[1] = m.specular.y; dm.specular[2] = m.specular.z;
+        dm.transmission[0] = m.transmission.x; dm.transmission[1] = m.transmission.y; dm.transmission[2] = m.transmission.z;
+        dm.emit[0] = m.emit_color.x; dm.emit[1] = m.emit_color.y; dm.emit[2] = m.emit_color.z;
+        dm.ior = m.ior;
+        dm.is_light = m.is_light;
+    }
+    out->info.material_count = world->mat_count;
+
+    // light list: packed (u32 ShapeType, pointer) pairs (push_light, parser.cpp:1144-1182).
+    // Only "is this entry a sphere" matters: it decides how many RNG steps
+    // sample_random_lights consumes (ray.cpp:542, 562).
+    out->light_is_sphere.clear();
+    const uint8_t *lb = (const uint8_t *)world->light_push_buffer.base;
+    const size_t stride = 4 + sizeof(void *);
+    for(size_t consumed = 0; lb && consumed + stride <= world->light_push_buffer.used; consumed += stride)
+    {
+        uint32_t type; memcpy(&type, lb + consumed, 4);
+        out->light_is_sphere.push_back(type == ORT_SHAPE_SPHERE ? 1 : 0);
+    }
+    if(out->light_is_sphere.size() != world->light_count)
+    {
+        *err = "light push buffer does not hold light_count entries";
+        return ORT_ERR_ARG;
+    }
+    out->info.light_count = world->light_count;
+    return ORT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// binary BVH, binned SAH
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Box
+{
+    float lo[3], hi[3];
+    void reset() { for(int k = 0; k < 3; ++k) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; } }
+    void grow(const float *l, const float *h) { for(int k = 0; k < 3; ++k) { if(l[k] < lo[k]) lo[k] = l[k]; if(h[k] > hi[k]) hi[k] = h[k]; } }
+    void grow_pt(const float *c) { for(int k = 0; k < 3; ++k) { if(c[k] < lo[k]) lo[k] = c[k]; if(c[k] > hi[k]) hi[k] = c[k]; } }
+    double area() const
+    {
+        double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+        if(dx < 0 || dy < 0 || dz < 0) return 0.0;
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct B2Node
+{
+    Box box;
+    uint32_t left, right;     // children (inner)
+    uint32_t first, count;    // leaf range in the index permutation (count > 0 = leaf)
+};
+
+struct Builder
+{
+    const std::vector<HostPrim> &prims;
+    const BuildOptions &opt;
+    std::vector<uint32_t> idx;
+    std::vector<float> cen;        // 3 per prim
+    std::vector<B2Node> nodes;
+
+    Builder(const std::vector<HostPrim> &p, const BuildOptions &o) : prims(p), opt(o) {}
+
+    void build()
+    {
+        size_t n = prims.size();
+        idx.resize(n); cen.resize(3 * n);
+        for(size_t i = 0; i < n; ++i)
+        {
+            idx[i] = (uint32_t)i;
+            for(int k = 0; k < 3; ++k) cen[3 * i + k] = 0.5f * (prims[i].lo[k] + prims[i].hi[k]);
+        }
+        nodes.reserve(2 * n + 1);
+        nodes.push_back(B2Node());
+        struct Job { uint32_t node, first, count; };
+        std::vector<Job> stack;
+        stack.push_back(Job{ 0u, 0u, (uint32_t)n });
+        const int NBINS = 16;
+        while(!stack.empty())
+        {
+            Job job = stack.back(); stack.pop_back();
+            Box box, cbox; box.reset(); cbox.reset();
+            for(uint32_t i = job.first; i < job.first + job.count; ++i)
+            {
+                const HostPrim &p = prims[idx[i]];
+                box.grow(p.lo, p.hi);
+                cbox.grow_pt(&cen[3 * idx[i]]);
+            }
+            B2Node &nd = nodes[job.node];
+            nd.box = box; nd.left = nd.right = 0; nd.first = job.first; nd.count = job.count;
+            if(job.count <= 1) continue;
+
+            // best binned split
+            double best_cost = 1e300; int best_axis = -1, best_bin = -1;
+            double parent_area = box.area();
+            for(int axis = 0; axis < 3; ++axis)
+            {
+                float c0 = cbox.lo[axis], c1 = cbox.hi[axis];
+                if(!(c1 > c0)) continue;
+                Box bins[NBINS]; uint32_t cnt[NBINS];
+                for(int b = 0; b < NBINS; ++b) { bins[b].reset(); cnt[b] = 0; }
+                float scale = (float)NBINS / (c1 - c0);
+                for(uint32_t i = job.first; i < job.first + job.count; ++i)
+                {
+                    uint32_t pi = idx[i];
+                    int b = (int)((cen[3 * pi + axis] - c0) * scale);
+                    if(b < 0) b = 0; if(b >= NBINS) b = NBINS - 1;
+                    bins[b].grow(prims[pi].lo, prims[pi].hi); cnt[b]++;
+                }
+                double la[NBINS]; uint32_t ln[NBINS];
+                Box acc; acc.reset(); uint32_t c = 0;
+                for(int b = 0; b < NBINS - 1; ++b)
+                {
+                    if(cnt[b]) acc.grow(bins[b].lo, bins[b].hi);
+                    c += cnt[b]; la[b] = acc.area(); ln[b] = c;
+                }
+                acc.reset(); c = 0;
+                for(int b = NBINS - 1; b > 0; --b)
+                {
+                    if(cnt[b]) acc.grow(bins[b].lo, bins[b].hi);
+                    c += cnt[b];
+                    if(ln[b - 1] == 0 || c == 0) continue;
+                    double cost = la[b - 1] * ln[b - 1] + acc.area() * c;
+                    if(cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+                }
+            }
+            double leaf_cost = (double)job.count;
+            double split_cost = (best_axis >= 0 && parent_area > 0.0) ? opt.traversal_cost + best_cost / parent_area : 1e300;
+            if(job.count <= opt.max_leaf && leaf_cost <= split_cost) continue;   // leaf
+
+            uint32_t mid;
+            if(best_axis >= 0)
+            {
+                float c0 = cbox.lo[best_axis], c1 = cbox.hi[best_axis];
+                float scale = (float)NBINS / (c1 - c0);
+                uint32_t *b = &idx[job.first], *e = b + job.count;
+                int axis = best_axis, bin = best_bin;
+                uint32_t *m = std::partition(b, e, [&](uint32_t pi)
+                {
+                    int bb = (int)((cen[3 * pi + axis] - c0) * scale);
+                    if(bb < 0) bb = 0; if(bb >= NBINS) bb = NBINS - 1;
+                    return bb < bin;
+                });
+                mid = (uint32_t)(m - &idx[0]);
+            }
+            else
+            {
+                // all centroids coincide: split the range in the middle
+                mid = job.first + job.count / 2;
+            }
+            if(mid == job.first || mid == job.first + job.count) mid = job.first + job.count / 2;
+
+            uint32_t l = (uint32_t)nodes.size();
+            nodes.push_back(B2Node()); nodes.push_back(B2Node());
+            B2Node &nd2 = nodes[job.node];   // re-fetch: push_back may have moved the storage
+            nd2.left = l; nd2.right = l + 1; nd2.count = 0;
+            stack.push_back(Job{ l + 1, mid, job.first + job.count - mid });
+            stack.push_back(Job{ l, job.first, mid - job.first });
+        }
+    }
+};
+
+// per-axis power-of-two grid step: smallest 2^e with 255 * 2^e >= extent
+inline int grid_exponent(double extent)
+{
+    if(!(extent > 0.0)) return -100;
+    int e = (int)ceil(log2(extent / 255.0));
+    if(e < -100) e = -100;
+    if(e > 120) e = 120;
+    return e;
+}
+
+} // namespace
+
+namespace {
+
+// builds one wide tree over `prims` and appends it to out->nodes / prims /
+// cylinders; the tree's root is the first node appended
+int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out,
+              uint32_t *depth_out, std::string *err)
+{
+    *depth_out = 1;
+    if(prims.empty())
+    {
+        // a single empty node: every ray misses
+        WideNode n; memset(&n, 0, sizeof(n));
+        n.ex = n.ey = n.ez = 127;
+        for(int s = 0; s < 8; ++s) { n.qlo_x[s] = n.qlo_y[s] = n.qlo_z[s] = 255; }
+        out->nodes.push_back(n);
+        return ORT_OK;
+    }
+
+    Builder b(prims, opt);
+    b.build();
+
+    struct WItem { uint32_t b2; uint32_t depth; };
+    std::deque<WItem> queue;
+    size_t next_out = out->nodes.size();     // index of the wide node being filled (BFS order == allocation order)
+    out->nodes.push_back(WideNode());
+    queue.push_back(WItem{ 0u, 1u });
+    uint32_t wide_depth = 0;
+
+    while(!queue.empty())
+    {
+        WItem it = queue.front(); queue.pop_front();
+        size_t self = next_out++;
+        if(it.depth > wide_depth) wide_depth = it.depth;
+
+        // gather up to 8 children by repeatedly opening the largest inner child
+        uint32_t kids[8]; int nk = 0;
+        const B2Node &rootn = b.nodes[it.b2];
+        if(rootn.count > 0) { kids[nk++] = it.b2; }             // degenerate: the whole (sub)tree is one leaf
+        else { kids[nk++] = rootn.left; kids[nk++] = rootn.right; }
+        for(;;)
+        {
+            if(nk >= 8) break;
+            int pick = -1; double pa = -1.0;
+            for(int i = 0; i < nk; ++i)
+            {
+                const B2Node &c = b.nodes[kids[i]];
+                if(c.count == 0) { double a = c.box.area(); if(a > pa) { pa = a; pick = i; } }
+            }
+            if(pick < 0) break;
+            const B2Node &c = b.nodes[kids[pick]];
+            kids[pick] = c.left;
+            kids[nk++] = c.right;
+        }
+
+        Box nb; nb.reset();
+        for(int i = 0; i < nk; ++i) nb.grow(b.nodes[kids[i]].box.lo, b.nodes[kids[i]].box.hi);
+
+        // octant slots: greedy assignment maximising (centroid - centre) . octant direction
+        int slot_of[8]; bool slot_used[8] = { false }; bool kid_done[8] = { false };
+        double ctr[3]; for(int k = 0; k < 3; ++k) ctr[k] = 0.5 * ((double)nb.lo[k] + nb.hi[k]);
+        for(int round = 0; round < nk; ++round)
+        {
+            double bestc = -1e300; int bi = -1, bs = -1;
+            for(int i = 0; i < nk; ++i)
+            {
+                if(kid_done[i]) continue;
+                const Box &cb = b.nodes[kids[i]].box;
+                double dc[3]; for(int k = 0; k < 3; ++k) dc[k] = 0.5 * ((double)cb.lo[k] + cb.hi[k]) - ctr[k];
+                for(int s = 0; s < 8; ++s)
+                {
+                    if(slot_used[s]) continue;
+                    double c = ((s & 1) ? dc[0] : -dc[0]) + ((s & 2) ? dc[1] : -dc[1]) + ((s & 4) ? dc[2] : -dc[2]);
+                    if(c > bestc) { bestc = c; bi = i; bs = s; }
+                }
+            }
+            slot_of[bi] = bs; slot_used[bs] = true; kid_done[bi] = true;
+        }
+        int kid_at[8]; for(int s = 0; s < 8; ++s) kid_at[s] = -1;
+        for(int i = 0; i < nk; ++i) kid_at[slot_of[i]] = i;
+
+        WideNode n; memset(&n, 0, sizeof(n));
+        n.px = nb.lo[0]; n.py = nb.lo[1]; n.pz = nb.lo[2];
+        int e[3]; double step[3];
+        for(int k = 0; k < 3; ++k) e[k] = grid_exponent((double)nb.hi[k] - nb.lo[k]);
+        // quantise outward; if rounding pushes a plane past 255, coarsen the grid
+        uint8_t qlo[3][8], qhi[3][8];
+        for(int k = 0; k < 3; ++k)
+        {
+            for(;;)
+            {
+                step[k] = ldexp(1.0, e[k]);
+                bool ok = true;
+                for(int s = 0; s < 8 && ok; ++s)
+                {
+                    if(kid_at[s] < 0) { qlo[k][s] = 255; qhi[k][s] = 0; continue; }
+                    const Box &cb = b.nodes[kids[kid_at[s]]].box;
+                    double lo = floor(((double)cb.lo[k] - (double)nb.lo[k]) / step[k]);
+                    double hi = ceil(((double)cb.hi[k] - (double)nb.lo[k]) / step[k]);
+                    if(lo < 0.0) lo = 0.0;
+                    if(hi > 255.0) { ok = false; break; }
+                    if(hi < lo) hi = lo;
+                    qlo[k][s] = (uint8_t)lo; qhi[k][s] = (uint8_t)hi;
+                }
+                if(ok) break;
+                e[k]++;
+            }
+        }
+        n.ex = (uint8_t)(e[0] + 127); n.ey = (uint8_t)(e[1] + 127); n.ez = (uint8_t)(e[2] + 127);
+        for(int s = 0; s < 8; ++s)
+        {
+            n.qlo_x[s] = qlo[0][s]; n.qlo_y[s] = qlo[1][s]; n.qlo_z[s] = qlo[2][s];
+            n.qhi_x[s] = qhi[0][s]; n.qhi_y[s] = qhi[1][s]; n.qhi_z[s] = qhi[2][s];
+        }
+
+        n.child_base = (uint32_t)out->nodes.size();
+        n.prim_base = (uint32_t)out->prims.size();
+        uint32_t prim_off = 0;
+        for(int s = 0; s < 8; ++s)
+        {
+            if(kid_at[s] < 0) continue;
+            const B2Node &c = b.nodes[kids[kid_at[s]]];
+            if(c.count == 0)
+            {
+                n.imask |= (uint8_t)(1u << s);
+                n.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+                out->nodes.push_back(WideNode());
+                queue.push_back(WItem{ kids[kid_at[s]], it.depth + 1 });
+            }
+            else
+            {
+                if(c.count > 3 || prim_off + c.count > 24) { *err = "internal: leaf too large"; return ORT_ERR_LIMIT; }
+                uint32_t unary = (1u << c.count) - 1u;
+                n.meta[s] = (uint8_t)((unary << 5) | prim_off);
+                for(uint32_t i = 0; i < c.count; ++i)
+                {
+                    const HostPrim &hp = prims[b.idx[c.first + i]];
+                    PrimRec r; memset(&r, 0, sizeof(r));
+                    r.rank = hp.rank; r.mat = hp.mat;
+                    r.ax = hp.a.x; r.ay = hp.a.y; r.az = hp.a.z;
+                    switch(hp.kind)
+                    {
+                        case PRIM_TRIANGLE:
+                            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z;
+                            r.cx = hp.c.x; r.cy = hp.c.y; r.cz = hp.c.z;
+                            r.kind = PRIM_TRIANGLE;
+                            break;
+                        case PRIM_SPHERE:
+                            r.bx = hp.radius; r.kind = PRIM_SPHERE;
+                            break;
+                        case PRIM_AAB:
+                            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z; r.kind = PRIM_AAB;
+                            break;
+                        case PRIM_CYLINDER:
+                        {
+                            CylinderAux ca; memset(&ca, 0, sizeof(ca));
+                            exact::m3 rot = exact::rotation_matrix_along_z(hp.b);     // ray.cpp:295
+                            ca.base[0] = hp.a.x; ca.base[1] = hp.a.y; ca.base[2] = hp.a.z;
+                            ca.axis_len = length(hp.b);                               // ray.cpp:302
+                            ca.radius = hp.radius;
+                            ca.r0[0] = rot.r0.x; ca.r0[1] = rot.r0.y; ca.r0[2] = rot.r0.z;
+                            ca.r1[0] = rot.r1.x; ca.r1[1] = rot.r1.y; ca.r1[2] = rot.r1.z;
+                            ca.r2[0] = rot.r2.x; ca.r2[1] = rot.r2.y; ca.r2[2] = rot.r2.z;
+                            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z;
+                            r.kind = PRIM_CYLINDER | ((uint32_t)out->cylinders.size() << 8);
+                            out->cylinders.push_back(ca);
+                        } break;
+                    }
+                    out->prims.push_back(r);
+                }
+                prim_off += c.count;
+            }
+        }
+        out->nodes[self] = n;
+    }
+
+    *depth_out = wide_depth;
+    return ORT_OK;
+}
+
+} // namespace
+
+int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, std::string *err)
+{
+    out->nodes.clear(); out->prims.clear(); out->cylinders.clear();
+    out->wide_depth = 0;
+    out->main_root = 0;
+    if(opt.max_leaf < 1 || opt.max_leaf > 3) { *err = "max_leaf must be 1..3"; return ORT_ERR_ARG; }
+
+    // pad the primitive boxes (see bvh.h: conservative culling)
+    double scene_abs = 0.0;
+    for(size_t i = 0; i < prims.size(); ++i)
+        for(int k = 0; k < 3; ++k)
+        {
+            scene_abs = std::max(scene_abs, fabs((double)prims[i].lo[k]));
+            scene_abs = std::max(scene_abs, fabs((double)prims[i].hi[k]));
+        }
+    std::vector<HostPrim> spheres, others;
+    for(size_t i = 0; i < prims.size(); ++i)
+    {
+        HostPrim &p = prims[i];
+        if(p.kind == PRIM_SPHERE)
+        {
+            // A ray TANGENT to a sphere (|b^2 - a*c| < 1e-5) is reported by the
+            // reference at t = -b/(2a) (ray.cpp:174-183), i.e. HALF WAY to the
+            // sphere, outside any static bound.  Spheres therefore live in their
+            // own tree that is traversed without clipping to the best hit so far
+            // (bvh.h), and their boxes cover every line that can pass the tangent
+            // test: radius sqrt(r^2 + 1e-5/a) with a = |dir|^2 >= 1/4.
+            double r = fabs((double)p.radius), rr = sqrt(r * r + 4e-5);
+            for(int k = 0; k < 3; ++k)
+            {
+                double c = k == 0 ? p.a.x : (k == 1 ? p.a.y : p.a.z);
+                p.lo[k] = (float)(c - rr); p.hi[k] = (float)(c + rr);
+            }
+        }
+        double dx = (double)p.hi[0] - p.lo[0], dy = (double)p.hi[1] - p.lo[1], dz = (double)p.hi[2] - p.lo[2];
+        double pad = opt.pad_rel * sqrt(dx * dx + dy * dy + dz * dz) + opt.pad_scene * scene_abs;
+        for(int k = 0; k < 3; ++k)
+        {
+            p.lo[k] = nextafterf((float)((double)p.lo[k] - pad), -INFINITY);
+            p.hi[k] = nextafterf((float)((double)p.hi[k] + pad), INFINITY);
+        }
+        if(p.kind == PRIM_SPHERE) spheres.push_back(p); else others.push_back(p);
+    }
+    std::vector<HostPrim>().swap(prims);
+    out->prims.reserve(spheres.size() + others.size());
+
+    uint32_t d0 = 0, d1 = 0;
+    if(!spheres.empty())
+    {
+        int rc = emit_tree(spheres, opt, out, &d0, err);
+        if(rc != ORT_OK) return rc;
+    }
+    out->main_root = (uint32_t)out->nodes.size();
+    int rc = emit_tree(others, opt, out, &d1, err);
+    if(rc != ORT_OK) return rc;
+    out->wide_depth = std::max(d0, d1);
+    // every level pushes at most one pending node group; +1 for the sphere tree's root entry
+    if(out->wide_depth + 1 > ORT_STACK_SIZE)
+    {
+        *err = "wide BVH deeper than the traversal stack";
+        return ORT_ERR_LIMIT;
+    }
+    out->info.bvh_node_count = (uint32_t)out->nodes.size();
+    out->info.bvh_node_bytes = (uint32_t)sizeof(WideNode);
+    return ORT_OK;
+}
+
+} // namespace ort

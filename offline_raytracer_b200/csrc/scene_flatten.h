@@ -1,0 +1,71 @@
+// scene_flatten.h -- host side of ort_scene_create: walks the reference's octree,
+// ranks its leaf records, builds the wide BVH and produces the arrays that are
+// uploaded to HBM (layout in bvh.h).
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "bvh.h"
+#include "ort_b200.h"
+
+namespace ort {
+
+// one leaf record of the octree (code/ray.cpp:637-774), decoded
+struct HostPrim
+{
+    uint32_t kind;      // PRIM_*
+    uint32_t rank;      // reference test order (see bvh.h)
+    uint32_t mat;
+    f3 a, b, c;
+    float radius;       // sphere / cylinder
+    float lo[3], hi[3]; // conservative, padded bounds
+};
+
+// device material, 64 B = 4 x 16 B (OrtMaterial re-packed for 128-bit loads)
+struct alignas(16) DevMaterial
+{
+    float diffuse[3];      int32_t is_light;
+    float specular[3];     float ior;
+    float transmission[3]; float pad0;
+    float emit[3];         float pad1;
+};
+static_assert(sizeof(DevMaterial) == 64, "DevMaterial is 4 x 16 B");
+
+struct BuildOptions
+{
+    float traversal_cost;   // SAH cost of visiting a (wide) node relative to one primitive test
+    uint32_t max_leaf;      // primitives per leaf child, <= 3
+    float pad_rel;          // box padding relative to the primitive's own extent
+    float pad_scene;        // box padding relative to the scene's largest |coordinate|
+    BuildOptions() : traversal_cost(0.5f), max_leaf(3), pad_rel(1e-3f), pad_scene(4e-6f) {}
+};
+
+struct FlatScene
+{
+    std::vector<WideNode> nodes;
+    std::vector<PrimRec> prims;
+    std::vector<CylinderAux> cylinders;
+    std::vector<DevMaterial> materials;
+    std::vector<uint8_t> light_is_sphere;   // one entry per light-list entry (parser.cpp:1144-1182)
+    OrtSceneInfo info;
+    uint32_t wide_depth;
+    uint32_t main_root;     // nodes [0, main_root) = sphere tree (absent if 0), main tree from main_root
+};
+
+// decode the octree into ranked records (+ world materials / light list)
+int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
+                    std::vector<HostPrim> *prims, FlatScene *out, std::string *err);
+// build the wide BVH over `prims` (consumed) into out->nodes / prims / cylinders
+int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, std::string *err);
+
+inline int flatten_scene(const OrtWorld *world, const OrtBVHOctreeNode *root, const BuildOptions &opt,
+                         FlatScene *out, std::string *err)
+{
+    std::vector<HostPrim> prims;
+    int rc = collect_records(world, root, &prims, out, err);
+    if(rc != ORT_OK) return rc;
+    return build_wide_bvh(prims, opt, out, err);
+}
+
+} // namespace ort
