@@ -48,6 +48,10 @@ typedef struct OrtHostScene OrtHostScene; /* host scene built by this library's 
 const char *ort_last_error(void);
 /* 0 when a usable CUDA device exists, else ORT_ERR_CUDA. */
 int ort_device_count(int *count);
+/* Measures the FP32-pipe roofline denominator of `device`: TFLOP/s of a dependent-chain
+ * FMUL+FADD kernel (no FMA contraction -- the instruction mix of the intersectors).
+ * MEASURED_PEAKS.json carries no FP32 figure.  The third argument is unused. */
+int ort_measure_fp32_peak(int device, float *tflops_non_fma, float *reserved);
 
 /* ------------------------------------------------------------------------
  * Scene hand-off.

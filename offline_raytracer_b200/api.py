@@ -139,6 +139,15 @@ def device_count():
     return n.value if rc == 0 else 0
 
 
+def measure_fp32_peak(device=0):
+    """TFLOP/s of the FMUL+FADD (non-FMA) chain microbenchmark: the FP32 roofline denominator"""
+    L = lib()
+    L.ort_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(c_f), C.POINTER(c_f)]
+    v = c_f(0)
+    _check(L.ort_measure_fp32_peak(device, C.byref(v), None))
+    return float(v.value)
+
+
 def default_params(width, height, spp, rr=0.8, seed=1234567, chunk_spp=0, kernel=ORT_KERNEL_DEFAULT):
     p = RenderParams()
     lib().ort_render_params_default(C.byref(p), width, height, spp)

@@ -254,6 +254,25 @@ __global__ void k_resolve_fixed(const long long *__restrict__ accum, float *__re
         rgb[3 * pix + k] = (float)((double)accum[4 * pix + k] * inv) / (float)spp;
 }
 
+// FP32-pipe roofline denominator (MEASURED_PEAKS.json has no FP32 figure).
+// Eight independent multiply-add chains per thread; with -fmad=false each `a*b+c` is
+// an FMUL and an FADD, i.e. the same non-FMA instruction mix the intersectors issue.
+// flops = threads * iters * 8 chains * 2.
+__global__ void __launch_bounds__(256)
+k_fp32_peak(float *out, int iters, float b, float c)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+#pragma unroll 4
+    for(int i = 0; i < iters; ++i)
+    {
+        a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+        a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+    }
+    float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if(s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;      // never true; keeps the chains alive
+}
+
 __global__ void k_zero_u64(unsigned long long *p, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

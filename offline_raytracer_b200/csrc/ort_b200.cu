@@ -215,6 +215,39 @@ int ort_device_count(int *count)
     return ORT_OK;
 }
 
+int ort_measure_fp32_peak(int device, float *tflops_non_fma, float *sm_clock_mhz_unused)
+{
+    (void)sm_clock_mhz_unused;
+    if(!tflops_non_fma) return fail(ORT_ERR_ARG, "null argument");
+    int n = 0;
+    if(ort_device_count(&n) != ORT_OK) return ORT_ERR_CUDA;
+    if(device < 0 || device >= n) return fail(ORT_ERR_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float *d_out = 0;
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    CUDA_TRY(cudaMalloc((void **)&d_out, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    float best = 0.f;
+    for(int rep = 0; rep < 5; ++rep)
+    {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        k_fp32_peak<<<blocks, threads>>>(d_out, iters, 0.999f, 0.001f);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = (double)blocks * threads * (double)iters * 16.0;
+        float tf = (float)(flops / (ms * 1e-3) / 1e12);
+        if(rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops_non_fma = best;
+    return ORT_OK;
+}
+
 int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, OrtScene **scene_out)
 {
     if(!scene_out) return fail(ORT_ERR_ARG, "scene_out is null");

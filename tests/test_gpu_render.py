@@ -1,0 +1,180 @@
+"""GPU parity of the whole radiance loop through the C ABI (ort_render / ort_tiled_raytrace_bvh /
+ort_render_accumulate_device) against the CPU oracle on identical per-pixel xorshift seeds.
+
+Tolerances (floating point, stated here as the spec requires):
+  * same seeds: the GPU consumes every stream in the reference's draw order; only libm
+    (sinf/cosf/atan2f/powf/logf) differs, so almost all pixels agree to ~1e-6 and a few
+    diverge after a discontinuity.  Required: >= 99.5 % of pixels within 1e-4 relative,
+    per-channel RMSE <= 0.25 x the oracle's own seed-to-seed RMSE, mean luminance within 0.5 %.
+  * different seeds (the converged-image criterion of SURVEY.md 8d): per-channel RMSE
+    <= 1.25 x RMSE(oracle seed A, oracle seed B), mean luminance within 2 %.
+Integer-side properties (tiling, chunking, multi-call accumulation) are bit-exact.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+W, H, SPP = 480, 270, 16          # BASELINE config 1
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def lum(img):
+    return float((img * np.array([0.2126, 0.7152, 0.0722], np.float32)).sum(-1).mean())
+
+
+def rmse(a, b):
+    return np.sqrt(((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean((0, 1)))
+
+
+@pytest.fixture(scope="module")
+def gpu_scene(ort, testscene_host):
+    sc = ort.Scene(testscene_host.world, testscene_host.root, 0)
+    yield sc
+    sc.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_images(testscene_host, testscene_oracle):
+    a, cnt = testscene_oracle.render(testscene_host.camera, ol.default_params(W, H, SPP, seed=1234567), threads=os.cpu_count())
+    b, _ = testscene_oracle.render(testscene_host.camera, ol.default_params(W, H, SPP, seed=7654321), threads=os.cpu_count())
+    return a, b, cnt
+
+
+def test_config1_same_seeds(ort, gpu_scene, testscene_host, oracle_images):
+    img_a, img_b, cnt = oracle_images
+    g, st = gpu_scene.render(testscene_host.camera, ort.default_params(W, H, SPP, seed=1234567))
+    assert st["samples"] == W * H * SPP
+    assert abs(st["rays"] - cnt["rays"]) < 2e-4 * cnt["rays"]
+    assert 3.5 < st["rays"] / st["samples"] < 5.5
+    close = (np.abs(g - img_a) <= 1e-4 * np.maximum(np.abs(img_a), 1e-3)).all(axis=2).mean()
+    assert close >= 0.995, close
+    noise = rmse(img_a, img_b)
+    assert np.all(rmse(g, img_a) <= 0.25 * noise), (rmse(g, img_a), noise)
+    assert abs(lum(g) - lum(img_a)) <= 0.005 * lum(img_a)
+    assert not np.isnan(g).any()
+
+
+def test_config1_converged_image_criterion(ort, gpu_scene, testscene_host, oracle_images):
+    img_a, img_b, _ = oracle_images
+    g, _ = gpu_scene.render(testscene_host.camera, ort.default_params(W, H, SPP, seed=7654321))
+    noise = rmse(img_a, img_b)
+    assert np.all(rmse(g, img_a) <= 1.25 * noise), (rmse(g, img_a), noise)
+    assert abs(lum(g) - lum(img_a)) <= 0.02 * lum(img_a)
+    # and against the golden showcase mean: (0.3254, 0.3032, 0.3747) +- 3 %
+    assert np.all(np.abs(g.mean((0, 1)) - np.array([0.3254, 0.3032, 0.3747])) < 0.03 * np.array([0.3254, 0.3032, 0.3747]))
+
+
+def test_chunked_streams_vs_oracle(ort, gpu_scene, testscene_host, testscene_oracle):
+    w, h, spp, chunk = 160, 90, 12, 5          # ragged: chunks of 5, 5, 2
+    hs = ort.HostScene.load(os.path.join(ol.DATA_DIR, "testscene.scn"), ol.DATA_DIR, w, h)
+    o, _ = testscene_oracle.render(hs.camera, ol.default_params(w, h, spp, chunk_spp=chunk), threads=os.cpu_count())
+    g, st = gpu_scene.render(hs.camera, ort.default_params(w, h, spp, chunk_spp=chunk))
+    assert st["samples"] == w * h * spp
+    close = (np.abs(g - o) <= 1e-4 * np.maximum(np.abs(o), 1e-3)).all(axis=2).mean()
+    assert close >= 0.995, close
+    # the multi-chunk image is order-independent fixed point: bit-reproducible run to run
+    g2, _ = gpu_scene.render(hs.camera, ort.default_params(w, h, spp, chunk_spp=chunk))
+    assert np.array_equal(bits(g), bits(g2))
+
+
+def test_single_chunk_is_bit_reproducible(ort, gpu_scene, testscene_host):
+    P = ort.default_params(W, H, 4)
+    a, _ = gpu_scene.render(testscene_host.camera, P)
+    b, _ = gpu_scene.render(testscene_host.camera, P)
+    assert np.array_equal(bits(a), bits(b))
+
+
+def test_tiles_equal_whole_image(ort, gpu_scene, testscene_host):
+    """per-pixel streams: any tiling gives the same pixels, bit for bit (ragged tiles included)"""
+    P = ort.default_params(W, H, 4)
+    whole, _ = gpu_scene.render(testscene_host.camera, P)
+    tiled = np.full((H, W, 3), -1.0, np.float32)
+    for (x0, y0, x1, y1) in [(0, 0, 201, 133), (201, 0, W, 133), (0, 133, 77, H), (77, 133, W, H)]:
+        Q = ort.default_params(W, H, 4)
+        Q.tile_min_x, Q.tile_min_y, Q.tile_one_past_max_x, Q.tile_one_past_max_y = x0, y0, x1, y1
+        gpu_scene.render(testscene_host.camera, Q, out=tiled)
+    assert np.array_equal(bits(whole), bits(tiled))
+    # an empty tile writes nothing
+    Q = ort.default_params(W, H, 4)
+    Q.tile_min_x = Q.tile_one_past_max_x = 10
+    canvas = np.full((H, W, 3), 7.0, np.float32)
+    gpu_scene.render(testscene_host.camera, Q, out=canvas)
+    assert np.all(canvas == 7.0)
+
+
+def test_reference_signature_entry_point(ort, ref, data_dir):
+    """ort_tiled_raytrace_bvh: same argument list as the reference (ray.cpp:1178); scene built by the
+    UNMODIFIED reference code; compared with the unmodified tiled_raytrace_bvh run on 1x1 tiles"""
+    rs = ref.scene_load(os.path.join(data_dir, "testscene.scn"), data_dir, W, H)
+    sc = ort.Scene(rs.world, rs.root, 0)
+    rect = (160, 90, 320, 180)
+    canvas = np.full((H, W, 3), -2.0, np.float32)
+    series = np.array([424242], np.uint32)
+    work = sc.tiled_raytrace_bvh(rs.camera, canvas, W, H, rect[0], rect[1], rect[2], rect[3], series, 8, 0.8)
+    assert work > 0
+    assert series[0] == ref.xor_shift_32(424242)                  # advanced by one step
+    ref_img, _ = rs.render_pixel_seeds(424242, 8, rect=rect, threads=os.cpu_count())
+    tile_g = canvas[rect[1]:rect[3], rect[0]:rect[2]]
+    tile_r = ref_img[rect[1]:rect[3], rect[0]:rect[2]]
+    close = (np.abs(tile_g - tile_r) <= 1e-4 * np.maximum(np.abs(tile_r), 1e-3)).all(axis=2).mean()
+    assert close >= 0.995, close
+    outside = np.ones((H, W), bool); outside[rect[1]:rect[3], rect[0]:rect[2]] = False
+    assert np.all(canvas[outside] == -2.0)                         # only the tile's pixels are written
+    sc.close()
+
+
+def test_device_accumulate_chunk_ranges_sum_exactly(ort, gpu_scene, testscene_host):
+    """the multi-GPU path on one GPU: two 'ranks' render disjoint chunk ranges into int64 buffers,
+    the buffers are added (what ncclSum does) and resolved == the single-call image, bit for bit"""
+    import torch
+    w, h, spp, chunk = 160, 90, 12, 3
+    hs = ort.HostScene.load(os.path.join(ol.DATA_DIR, "testscene.scn"), ol.DATA_DIR, w, h)
+    whole, _ = gpu_scene.render(hs.camera, ort.default_params(w, h, spp, chunk_spp=chunk))
+    st = torch.cuda.current_stream().cuda_stream
+    acc = [torch.empty((h, w, 4), dtype=torch.int64, device="cuda:0") for _ in range(2)]
+    for rank, (b, e) in enumerate(((0, 2), (2, 4))):
+        gpu_scene.accum_zero_device(acc[rank].data_ptr(), w, h, stream=st)
+        P = ort.default_params(w, h, spp, chunk_spp=chunk)
+        P.chunk_begin, P.chunk_end = b, e
+        gpu_scene.render_accumulate_device(hs.camera, P, acc[rank].data_ptr(), stream=st)
+    total = acc[0] + acc[1]
+    rgb = torch.empty((h, w, 3), dtype=torch.float32, device="cuda:0")
+    gpu_scene.accum_resolve_device(total.data_ptr(), w, h, spp, rgb.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(rgb.cpu().numpy()), bits(whole))
+
+
+def test_own_scene_image_vs_oracle(ort, oracle):
+    hs = ort.HostScene.load(os.path.join(ol.SCENES_DIR, "box_spheres.scn"), ol.SCENES_DIR, 160, 90)
+    osc = oracle.scene(hs.world, hs.root)
+    sc = ort.Scene(hs.world, hs.root, 0)
+    o, _ = osc.render(hs.camera, ol.default_params(160, 90, 16), threads=os.cpu_count())
+    g, _ = sc.render(hs.camera, ort.default_params(160, 90, 16))
+    close = (np.abs(g - o) <= 1e-4 * np.maximum(np.abs(o), 1e-3)).all(axis=2).mean()
+    assert close >= 0.99, close          # glass + mirror paths amplify libm differences more than testscene
+    assert abs(lum(g) - lum(o)) <= 0.02 * lum(o)
+    sc.close()
+
+
+def test_bad_arguments(ort, gpu_scene, testscene_host):
+    P = ort.default_params(W, H, 4)
+    P.tile_one_past_max_x = W + 1
+    with pytest.raises(ort.OrtError, match="tile rect"):
+        gpu_scene.render(testscene_host.camera, P)
+    P = ort.default_params(W, H, 4)
+    P.ray_per_pixel_count = 0
+    with pytest.raises(ort.OrtError):
+        gpu_scene.render(testscene_host.camera, P)
+    P = ort.default_params(W, H, 4)
+    P.kernel = 77
+    with pytest.raises(ort.OrtError):
+        gpu_scene.render(testscene_host.camera, P)
