@@ -144,8 +144,13 @@ ORT_HD exact::Hit intersect_prim(const SceneView &s, uint32_t prim, f3 o, f3 d, 
 #define ORT_STACK_SIZE 32
 #endif
 
-// select byte k (0..3) of w as float
+// byte k (0..3) of w as a float, without the quarter-rate I2F conversion unit: PRMT builds
+// the bit pattern of 2^23 + byte, and subtracting 2^23 is exact.
+#if defined(__CUDA_ARCH__)
+ORT_HD float byte_f(uint32_t w, uint32_t k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k)) - 8388608.0f; }
+#else
 ORT_HD float byte_f(uint32_t w, uint32_t k) { return (float)((w >> (8u * k)) & 0xFFu); }
+#endif
 
 // Closest hit.  COUNT adds work counters (the counters build of the same code,
 // SURVEY.md 8d).  o/d as in raycast_top_most_node; d need not be unit.
@@ -202,6 +207,7 @@ ORT_HD void trace(const SceneView &s, f3 o, f3 d, TraceHit *hit, TraceCounters *
             ng_x = f2u(n1.x);
             tg_x = f2u(n1.y);
             uint32_t hitmask = 0u;
+            const uint32_t octinv4 = octinv * 0x01010101u;
 #pragma unroll
             for(int half = 0; half < 2; ++half)
             {
@@ -215,10 +221,15 @@ ORT_HD void trace(const SceneView &s, f3 o, f3 d, TraceHit *hit, TraceCounters *
                 uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
                 uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
                 uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+                // per byte: inner children (low 5 bits >= 24, i.e. bits 3 and 4 set) get their slot
+                // XORed with octinv so that the highest hit bit is the nearest child
+                uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
+                uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+                uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
                 for(uint32_t k = 0; k < 4; ++k)
                 {
-                    uint32_t meta = (meta4 >> (8u * k)) & 0xFFu;
                     float t0x = fmaf(byte_f(nearx, k), ax, bx);
                     float t0y = fmaf(byte_f(neary, k), ay, by);
                     float t0z = fmaf(byte_f(nearz, k), az, bz);
@@ -227,14 +238,10 @@ ORT_HD void trace(const SceneView &s, f3 o, f3 d, TraceHit *hit, TraceCounters *
                     float t1z = fmaf(byte_f(farz, k), az, bz);
                     float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
                     float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
-                    if(COUNT) { if(meta) cnt->box_tests++; }
-                    if(tmin <= tmax)
-                    {
-                        uint32_t child_bits = meta >> 5;
-                        uint32_t bit_index = meta & 31u;
-                        if(bit_index >= 24u) bit_index ^= octinv;
-                        hitmask |= child_bits << bit_index;
-                    }
+                    if(COUNT) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
+                    uint32_t child_bits = (child_bits4 >> (8u * k)) & 0xFFu;
+                    uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
+                    hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
                 }
             }
             ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);

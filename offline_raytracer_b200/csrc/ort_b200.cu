@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
+#include "wavefront.cuh"
 #include "scene_flatten.h"
 
 using namespace ort;
@@ -49,6 +49,10 @@ struct OrtScene
     cudaEvent_t ev0, ev1;
     int sm_count;
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
+    // wavefront path pool
+    WfBuffers wf;
+    unsigned int *d_active;             // per-iteration "slots still active" counters
+    unsigned int *h_active;             // pinned mirror
 
     SceneView view() const
     {
@@ -144,6 +148,69 @@ PathConsts make_consts(const OrtScene *s, const OrtCamera *cam, const OrtRenderP
     return c;
 }
 
+#define WF_BATCH 8
+
+int ensure_wavefront(OrtScene *s, uint32_t capacity)
+{
+    if(s->wf.capacity >= capacity) return ORT_OK;
+    cudaFree(s->wf.ray_o); cudaFree(s->wf.ray_d); cudaFree(s->wf.hit); cudaFree(s->wf.s_wo);
+    cudaFree(s->wf.s_w); cudaFree(s->wf.s_c); cudaFree(s->wf.s_chunk);
+    memset(&s->wf, 0, sizeof(s->wf));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.ray_o, (size_t)capacity * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.ray_d, (size_t)capacity * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.hit, (size_t)capacity * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.s_wo, (size_t)capacity * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.s_w, (size_t)capacity * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.s_c, (size_t)capacity * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.s_chunk, (size_t)capacity * sizeof(uint32_t)));
+    s->wf.capacity = capacity;
+    if(!s->d_active)
+    {
+        CUDA_TRY(cudaMalloc((void **)&s->d_active, WF_BATCH * sizeof(unsigned int)));
+        CUDA_TRY(cudaMallocHost((void **)&s->h_active, WF_BATCH * sizeof(unsigned int)));
+    }
+    return ORT_OK;
+}
+
+// Wavefront driver: reset -> shade (generates the first rays) -> { extend -> shade }* until no
+// slot is active.  The "still active" count of every iteration is read back once per WF_BATCH
+// iterations, so the host never waits on a single launch.
+int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint32_t *launches)
+{
+    uint32_t capacity = 1u << 21;
+    if(const char *e = getenv("ORT_WF_SLOTS")) { long v = atol(e); if(v >= 1024 && v <= (1l << 26)) capacity = (uint32_t)v; }
+    unsigned long long items128 = (a.total_items + 127ull) & ~127ull;
+    if(items128 < capacity) capacity = (uint32_t)items128;
+    int rc = ensure_wavefront(s, capacity);
+    if(rc != ORT_OK) return rc;
+    WfBuffers wf = s->wf;
+    wf.capacity = capacity;
+    const unsigned grid = (capacity + 127u) / 128u;
+    k_wf_reset<<<grid, 128, 0, stream>>>(wf);
+    CUDA_TRY(cudaMemsetAsync(s->d_active, 0, WF_BATCH * sizeof(unsigned int), stream));
+    k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active);
+    *launches += 2;
+    for(;;)
+    {
+        CUDA_TRY(cudaMemsetAsync(s->d_active, 0, WF_BATCH * sizeof(unsigned int), stream));
+        for(int it = 0; it < WF_BATCH; ++it)
+        {
+#ifdef ORT_COUNTERS
+            k_wf_extend<true><<<grid, 128, 0, stream>>>(a.scene, wf, a.stats);
+#else
+            k_wf_extend<false><<<grid, 128, 0, stream>>>(a.scene, wf, a.stats);
+#endif
+            k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active + it);
+        }
+        *launches += 2 * WF_BATCH;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(s->h_active, s->d_active, WF_BATCH * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if(s->h_active[WF_BATCH - 1] == 0) break;
+    }
+    return ORT_OK;
+}
+
 // launches the render kernels for the chunk range of P into accum (fixed point)
 // or rgb (single-chunk float mode); exactly one of the two is non-null
 int launch_render(OrtScene *s, const OrtCamera *cam, const OrtRenderParams *P, const ChunkPlan &cp,
@@ -151,8 +218,6 @@ int launch_render(OrtScene *s, const OrtCamera *cam, const OrtRenderParams *P, c
 {
     int tw = P->tile_one_past_max_x - P->tile_min_x, th = P->tile_one_past_max_y - P->tile_min_y;
     if(tw <= 0 || th <= 0 || cp.count == 0) return ORT_OK;
-    if(P->kernel == ORT_KERNEL_WAVEFRONT) return fail(ORT_ERR_ARG, "wavefront kernels are not built into this library yet");
-
     RenderArgs a;
     a.scene = s->view();
     a.pc = make_consts(s, cam, P);
@@ -167,6 +232,13 @@ int launch_render(OrtScene *s, const OrtCamera *cam, const OrtRenderParams *P, c
     a.accum = accum; a.rgb = rgb;
 
     CUDA_TRY(cudaMemsetAsync(s->d_stats + STAT_WORK_COUNTER, 0, sizeof(unsigned long long), stream));
+    uint32_t kernel = P->kernel;
+    if(kernel == ORT_KERNEL_DEFAULT)
+    {
+        const char *e = getenv("ORT_KERNEL");
+        kernel = (e && atoi(e) == ORT_KERNEL_MEGAKERNEL) ? ORT_KERNEL_MEGAKERNEL : ORT_KERNEL_WAVEFRONT;
+    }
+    if(kernel == ORT_KERNEL_WAVEFRONT) return launch_wavefront(s, a, stream, launches);
     if(s->mega_blocks_per_sm == 0)
     {
         int nb = 0;
@@ -300,6 +372,9 @@ int ort_scene_destroy(OrtScene *s)
     if(s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_cyl); cudaFree(s->d_materials);
     cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb);
+    cudaFree(s->wf.ray_o); cudaFree(s->wf.ray_d); cudaFree(s->wf.hit); cudaFree(s->wf.s_wo);
+    cudaFree(s->wf.s_w); cudaFree(s->wf.s_c); cudaFree(s->wf.s_chunk); cudaFree(s->d_active);
+    if(s->h_active) cudaFreeHost(s->h_active);
     if(s->ev0) cudaEventDestroy(s->ev0);
     if(s->ev1) cudaEventDestroy(s->ev1);
     if(s->stream) cudaStreamDestroy(s->stream);

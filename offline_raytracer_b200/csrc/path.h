@@ -109,9 +109,25 @@ ORT_HD void sample_random_lights_rng(const PathConsts &c, uint32_t *s)
 }
 
 // ---- BSDF --------------------------------------------------------------------
+// The reference calls powf with the constant exponents 5 and 4 and with base e
+// (ray.cpp:829, 857, 964-966).  On the device these are evaluated as repeated
+// multiplication and expf: the same functions to within the few ulps by which
+// CUDA's libm differs from glibc's anyway (path.h header), at a fraction of the
+// instructions and code size of the general powf.  The host build (tests/sim) keeps
+// powf so that it stays bit-identical to the oracle.
+#if defined(__CUDA_ARCH__)
+ORT_HD float pow5_ref(float x) { float x2 = x * x; return x2 * x2 * x; }
+ORT_HD float pow4_ref(float x) { float x2 = x * x; return x2 * x2; }
+ORT_HD float exp_ref(float y) { return expf(y); }
+#else
+ORT_HD float pow5_ref(float x) { return powf(x, 5.0f); }
+ORT_HD float pow4_ref(float x) { return powf(x, 4.0f); }
+ORT_HD float exp_ref(float y) { return powf(ORT_EULER, y); }
+#endif
+
 ORT_HD f3 fresnel(f3 Ks, float l_dot_h)                                  // ray.cpp:825-831
 {
-    return Ks + (1 - powf(1.0f - absolute(l_dot_h), 5.0f)) * (mk3(1.0f, 1.0f, 1.0f) - Ks);
+    return Ks + (1 - pow5_ref(1.0f - absolute(l_dot_h))) * (mk3(1.0f, 1.0f, 1.0f) - Ks);
 }
 
 ORT_HD float ggx_distribution(f3 N, f3 H, float roughness)               // ray.cpp:834-865
@@ -123,7 +139,7 @@ ORT_HD float ggx_distribution(f3 N, f3 H, float roughness)               // ray.
         float r2 = square(roughness);
         float tan_theta = sqrtf(1.0f - square(n_dot_h)) / n_dot_h;
         float nom = r2;
-        float denom = ORT_PI_32 * powf(n_dot_h, 4.0f) * square(r2 + square(tan_theta));
+        float denom = ORT_PI_32 * pow4_ref(n_dot_h) * square(r2 + square(tan_theta));
         if(!compare_equal_f32(denom, 0.0f)) result = nom / denom;
     }
     return result;
@@ -186,9 +202,9 @@ ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, f3 Kd, f3 Ks, f3 Kt, float ior, fl
         f3 At = mk3(1.0f, 1.0f, 1.0f);
         if(wo_dot_n < 0)
         {
-            At.x = powf(ORT_EULER, distance * logf(Kt.x));
-            At.y = powf(ORT_EULER, distance * logf(Kt.y));
-            At.z = powf(ORT_EULER, distance * logf(Kt.z));
+            At.x = exp_ref(distance * logf(Kt.x));
+            At.y = exp_ref(distance * logf(Kt.y));
+            At.z = exp_ref(distance * logf(Kt.z));
         }
         Beern bn = get_beer_n(N, wo, ior);
         f3 m = normalize(-(bn.ni * wi + bn.no * wo));

@@ -1,0 +1,228 @@
+// wavefront.cuh -- the wavefront form of the radiance loop (code/ray.cpp:1178-1466):
+// separate GENERATE / EXTEND / SHADE / ACCUMULATE stages over a pool of path slots that
+// lives in HBM, instead of one loop per pixel.
+//
+//   k_wf_reset    marks every slot FRESH
+//   k_wf_shade    per slot: SHADE the hit of the ray just extended (ray.cpp:1251-1277,
+//                 1355-1421), draw the roulette / light pick / BSDF sample of the next bounce
+//                 (ray.cpp:1280-1349); when the path ends: ACCUMULATE into the stream's sum
+//                 (ray.cpp:1257,1364), and GENERATE the next camera ray of the slot's sample
+//                 stream (ray.cpp:1215-1246) -- or pull the next (pixel, chunk) stream from the
+//                 global work counter.  A slot therefore always leaves this kernel holding a
+//                 ray (path regeneration), so the wavefront stays full until the work runs out
+//                 and no compaction pass is needed while it does.
+//   k_wf_extend   per slot: closest hit of its ray (bvh.h) -> (t, primitive)
+//
+// Why split: the single-kernel form is ~6000 SASS instructions (96 KB); ncu shows its
+// warps starved by instruction-cache misses (icc hit rate 64 %, "no_instruction" the top
+// stall) with 8 of 32 lanes active on average.  EXTEND alone is a 1600-instruction loop
+// that stays cache resident and runs at 8-10 Grays/s on the same rays.
+//
+// Slot state, structure-of-arrays, 16-byte records (one 128-bit access each):
+//   ray_o   origin.xyz | state word (low 2 bits: DEAD/ACTIVE/FRESH)
+//   ray_d   direction.xyz | -
+//   hit     t | primitive index                                   (8 bytes)
+//   s_wo    wo.xyz | xorshift state of the stream
+//   s_w     throughput weight.xyz | pixel index
+//   s_c     radiance sum of the stream so far .xyz | samples left (bit 31: ray is a primary)
+//   s_chunk chunk index of the stream                              (4 bytes)
+#pragma once
+
+#include "kernels.cuh"
+
+namespace ort {
+
+enum { WF_DEAD = 0u, WF_ACTIVE = 1u, WF_FRESH = 2u };
+
+struct WfBuffers
+{
+    float4 *ray_o, *ray_d;
+    uint2 *hit;
+    float4 *s_wo, *s_w, *s_c;
+    uint32_t *s_chunk;
+    uint32_t capacity;
+};
+
+__global__ void k_wf_reset(WfBuffers wf)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < wf.capacity) wf.ray_o[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_FRESH));
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_wf_extend(SceneView scene, WfBuffers wf, unsigned long long *stats)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long nodes = 0, boxes = 0, shapes = 0, rays = 0;
+    if(i < wf.capacity)
+    {
+        float4 ro = wf.ray_o[i];
+        if(__float_as_uint(ro.w) == WF_ACTIVE)
+        {
+            float4 rd = wf.ray_d[i];
+            TraceHit hit; TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
+            trace<COUNT>(scene, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), &hit, &cnt);
+            wf.hit[i] = make_uint2(__float_as_uint(hit.t), hit.prim);
+            rays = 1;
+            if(COUNT) { nodes = cnt.node_visits; boxes = cnt.box_tests; shapes = cnt.shape_tests; }
+        }
+    }
+    rays = warp_sum(rays);
+    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); shapes = warp_sum(shapes); }
+    if((threadIdx.x & 31) == 0 && rays)
+    {
+        atomicAdd(&stats[STAT_RAYS], rays);
+        if(COUNT)
+        {
+            atomicAdd(&stats[STAT_NODE_VISITS], nodes);
+            atomicAdd(&stats[STAT_BOX_TESTS], boxes);
+            atomicAdd(&stats[STAT_SHAPE_TESTS], shapes);
+        }
+    }
+}
+
+// material + normalised normal of the winning record (ray.cpp:817).  Triangles -- almost all
+// hits -- need only cross(e1, e2) of the stored vertices, the very value the intersector
+// returns (ray.cpp:110); the analytic shapes re-run their intersector.
+__device__ __forceinline__ void wf_finish_hit(const SceneView &s, uint32_t prim, f3 o, f3 d, uint32_t *mat, f3 *normal)
+{
+    if(prim == 0xFFFFFFFFu) { *mat = 0u; *normal = mk3(0.f, 0.f, 0.f); return; }
+    const q4 *p = s.prims + 3u * prim;
+    q4 A = ldq(p), B = ldq(p + 1), C = ldq(p + 2);
+    *mat = f2u(B.w);
+    if((f2u(C.w) & 0xFFu) == PRIM_TRIANGLE)
+    {
+        *normal = normalize(cross(q3(B) - q3(A), q3(C) - q3(A)));
+        return;
+    }
+    TraceHit h; h.t = 0.f; h.prim = prim; h.rank = 0u;
+    finish_hit(s, h, o, d, mat, normal);
+}
+
+__global__ void __launch_bounds__(128)
+k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n_samples = 0;
+    unsigned int still_active = 0;
+    if(i < wf.capacity)
+    {
+        float4 ro = wf.ray_o[i];
+        uint32_t state = __float_as_uint(ro.w);
+        if(state != WF_DEAD)
+        {
+            Path p;
+            f3 color = mk3(0.f, 0.f, 0.f);
+            uint32_t samples_left = 0, pixel_index = 0xFFFFFFFFu, chunk = 0;
+            bool have_ray = false;
+            if(state == WF_ACTIVE)
+            {
+                float4 rd = wf.ray_d[i], swo = wf.s_wo[i], sw = wf.s_w[i], scol = wf.s_c[i];
+                uint2 h = wf.hit[i];
+                chunk = wf.s_chunk[i];
+                p.origin = mk3(ro.x, ro.y, ro.z); p.dir = mk3(rd.x, rd.y, rd.z);
+                p.wo = mk3(swo.x, swo.y, swo.z); p.series = __float_as_uint(swo.w);
+                p.weight = mk3(sw.x, sw.y, sw.z); pixel_index = __float_as_uint(sw.w);
+                color = mk3(scol.x, scol.y, scol.z);
+                uint32_t sl = __float_as_uint(scol.w);
+                const bool primary = (sl >> 31) != 0u;
+                samples_left = sl & 0x7FFFFFFFu;
+                p.normal = mk3(0.f, 0.f, 0.f); p.mat = 0u;
+                uint32_t mat; f3 nrm;
+                wf_finish_hit(a.scene, h.y, p.origin, p.dir, &mat, &nrm);
+                float hit_t = __uint_as_float(h.x);
+                bool alive = primary ? shade_primary(a.pc, &p, hit_t, mat, nrm, &color)
+                                     : shade_bounce(a.pc, &p, hit_t, mat, nrm, &color);
+                have_ray = alive && next_bounce(a.pc, &p);
+            }
+            bool primary_next = false;
+            if(!have_ray)
+            {
+                bool dead = false;
+                if(samples_left == 0)
+                {
+                    // ---- accumulate the finished stream (ray.cpp:1428) ----
+                    if(pixel_index != 0xFFFFFFFFu)
+                    {
+                        if(a.accum)
+                        {
+                            unsigned long long *dst = (unsigned long long *)(a.accum + 4ull * pixel_index);
+                            atomicAdd(dst + 0, (unsigned long long)to_fixed(color.x));
+                            atomicAdd(dst + 1, (unsigned long long)to_fixed(color.y));
+                            atomicAdd(dst + 2, (unsigned long long)to_fixed(color.z));
+                        }
+                        else
+                        {
+                            f3 px = color / (float)a.spp;
+                            a.rgb[3ull * pixel_index + 0] = px.x;
+                            a.rgb[3ull * pixel_index + 1] = px.y;
+                            a.rgb[3ull * pixel_index + 2] = px.z;
+                        }
+                    }
+                    // ---- next stream from the global work counter ----
+                    int x = -1, y = -1;
+                    for(;;)
+                    {
+                        unsigned long long item = atomicAdd(a.work_counter, 1ull);
+                        if(item >= a.total_items) break;
+                        uint32_t lane = (uint32_t)(item & 31ull);
+                        unsigned long long blk = item >> 5;
+                        uint32_t bx = (uint32_t)(blk % a.blocks_x); blk /= a.blocks_x;
+                        uint32_t by = (uint32_t)(blk % a.blocks_y); blk /= a.blocks_y;
+                        int lx = (int)(bx * 8u + (lane & 7u)), ly = (int)(by * 4u + (lane >> 3));
+                        if(lx < a.tile_w && ly < a.tile_h)
+                        {
+                            x = a.tile_min_x + lx; y = a.tile_min_y + ly;
+                            chunk = a.chunk_begin + (uint32_t)blk;
+                            break;
+                        }
+                    }
+                    if(x < 0) dead = true;
+                    else
+                    {
+                        pixel_index = (uint32_t)(y * a.pc.width + x);
+                        samples_left = a.chunk_spp;
+                        if((chunk + 1u) * a.chunk_spp > a.spp) samples_left = a.spp - chunk * a.chunk_spp;
+                        p.series = ort_stream_seed(a.base_seed, pixel_index, chunk);
+                        color = mk3(0.f, 0.f, 0.f);
+                    }
+                }
+                if(dead)
+                {
+                    wf.ray_o[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_DEAD));
+                }
+                else
+                {
+                    // ---- generate (ray.cpp:1215-1246) ----
+                    int x = (int)(pixel_index % (uint32_t)a.pc.width), y = (int)(pixel_index / (uint32_t)a.pc.width);
+                    generate_primary(a.pc, pixel_focal_point(a.pc, x, y), &p);
+                    --samples_left;
+                    n_samples = 1;
+                    primary_next = true;
+                    have_ray = true;
+                }
+            }
+            if(have_ray)
+            {
+                wf.ray_o[i] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
+                wf.ray_d[i] = make_float4(p.dir.x, p.dir.y, p.dir.z, 0.f);
+                wf.s_wo[i] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
+                wf.s_w[i] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
+                wf.s_c[i] = make_float4(color.x, color.y, color.z,
+                                        __uint_as_float(samples_left | (primary_next ? 0x80000000u : 0u)));
+                wf.s_chunk[i] = chunk;
+                still_active = 1;
+            }
+        }
+    }
+    n_samples = warp_sum(n_samples);
+    still_active = __reduce_add_sync(0xFFFFFFFFu, still_active);
+    if((threadIdx.x & 31) == 0)
+    {
+        if(n_samples) atomicAdd(&a.stats[STAT_SAMPLES], n_samples);
+        if(still_active) atomicAdd(active_out, still_active);
+    }
+}
+
+} // namespace ort

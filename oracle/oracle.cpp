@@ -952,6 +952,61 @@ void oracle_render(void *h, const OrtCamera *cam, const OrtRenderParams *P, ort_
     if(counters) { counters[0] += c0.load(); counters[1] += c1.load(); counters[2] += c2.load(); counters[3] += c3.load(); }
 }
 
+// Same semantics as ort_render_accumulate_device (include/ort_b200.h): ADDS the fixed-point
+// chunk sums of [chunk_begin, chunk_end) into accum, an int64[height*width*4] buffer.
+void oracle_render_accum(void *h, const OrtCamera *cam, const OrtRenderParams *P, int64_t *accum, int n_threads)
+{
+    OracleScene *sc = (OracleScene *)h;
+    if(n_threads < 1) n_threads = 1;
+    u32 spp = P->ray_per_pixel_count;
+    u32 chunk_spp = P->chunk_spp ? P->chunk_spp : spp;
+    if(chunk_spp > spp) chunk_spp = spp;
+    u32 n_chunks = spp ? (spp + chunk_spp - 1) / chunk_spp : 0;
+    u32 c_begin = P->chunk_begin, c_end = P->chunk_end;
+    if(c_begin == 0 && c_end == 0) c_end = n_chunks;
+    if(c_end > n_chunks) c_end = n_chunks;
+    std::atomic<int> next_row(P->tile_min_y);
+    auto work = [&]()
+    {
+        std::vector<const OrtBVHOctreeNode *> queue;
+        Counters cnt = { 0, 0, 0, 0 };
+        for(;;)
+        {
+            int y = next_row.fetch_add(1);
+            if(y >= P->tile_one_past_max_y) break;
+            for(int x = P->tile_min_x; x < P->tile_one_past_max_x; ++x)
+            {
+                u32 pixel_index = (u32)(y * P->output_width + x);
+                int64_t *dst = accum + 4 * (size_t)pixel_index;
+                for(u32 c = c_begin; c < c_end; ++c)
+                {
+                    u32 n = chunk_spp;
+                    if((c + 1) * chunk_spp > spp) n = spp - c * chunk_spp;
+                    u32 series = ort_stream_seed(P->base_seed, pixel_index, c);
+                    V3 color = trace_stream(*sc, cam, P, x, y, &series, n, queue, &cnt, 0);
+                    dst[0] += to_fixed(color.x); dst[1] += to_fixed(color.y); dst[2] += to_fixed(color.z);
+                }
+            }
+        }
+    };
+    std::vector<std::thread> threads;
+    for(int i = 1; i < n_threads; ++i) threads.emplace_back(work);
+    work();
+    for(auto &t : threads) t.join();
+}
+
+// resolve of the fixed-point buffer, as ort_accum_resolve_device
+void oracle_accum_resolve(const int64_t *accum, int width, int height, uint32_t spp, ort_v3 *out)
+{
+    const double inv = 1.0 / (double)(1 << ORT_ACCUM_FRAC_BITS);
+    for(size_t i = 0; i < (size_t)width * height; ++i)
+    {
+        out[i].x = (f32)((double)accum[4 * i + 0] * inv) / (f32)spp;
+        out[i].y = (f32)((double)accum[4 * i + 1] * inv) / (f32)spp;
+        out[i].z = (f32)((double)accum[4 * i + 2] * inv) / (f32)spp;
+    }
+}
+
 // ---- single functions, same signatures as oracle/_ref's ref_* --------------
 static void pack_isect(Isect r, float *out)
 {

@@ -299,6 +299,8 @@ class Oracle(_FuncsMixin):
         lib.oracle_scene_records.argtypes = [vp, vp, vp]
         lib.oracle_raycast_batch.argtypes = [vp, c_u64, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
         lib.oracle_render.argtypes = [vp, vp, C.POINTER(RenderParams), vp, vp, C.c_int, C.c_int]
+        lib.oracle_render_accum.argtypes = [vp, vp, C.POINTER(RenderParams), vp, C.c_int]
+        lib.oracle_accum_resolve.argtypes = [vp, C.c_int, C.c_int, c_u32, vp]
         lib.oracle_to_fixed.argtypes = [c_f]
         lib.oracle_to_fixed.restype = C.c_int64
         self._bind_funcs(lib, "oracle_")
@@ -348,6 +350,17 @@ class OracleScene:
 
     def sample_random_lights(self, state):
         return int(self.o.lib.oracle_sample_random_lights(self.h, c_u32(state)))
+
+    def render_accum(self, camera_ptr, params, accum, threads=8):
+        """adds the fixed-point chunk sums of params' chunk range into accum (int64 [H, W, 4])"""
+        assert accum.dtype == np.int64 and accum.flags["C_CONTIGUOUS"]
+        self.o.lib.oracle_render_accum(self.h, camera_ptr, C.byref(params), _ptr(accum), threads)
+
+    def accum_resolve(self, accum, spp):
+        H, W = accum.shape[:2]
+        out = np.zeros((H, W, 3), np.float32)
+        self.o.lib.oracle_accum_resolve(_ptr(accum), W, H, spp, _ptr(out))
+        return out
 
 
 def stream_seed(base, pixel_index, chunk):
