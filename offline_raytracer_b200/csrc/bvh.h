@@ -152,130 +152,157 @@ ORT_HD float byte_f(uint32_t w, uint32_t k) { return __uint_as_float(__byte_perm
 ORT_HD float byte_f(uint32_t w, uint32_t k) { return (float)((w >> (8u * k)) & 0xFFu); }
 #endif
 
+// traversal stack of pending node groups: a per-thread array here; the wavefront extend
+// kernel substitutes a shared-memory column (wavefront.cuh)
+struct LocalStack
+{
+    uint32_t x[ORT_STACK_SIZE], y[ORT_STACK_SIZE];
+    ORT_HD void put(int i, uint32_t a, uint32_t b) { x[i] = a; y[i] = b; }
+    ORT_HD void get(int i, uint32_t &a, uint32_t &b) const { a = x[i]; b = y[i]; }
+};
+
+// state of one ray's traversal, so that a kernel can interleave rays step by step
+struct Trav
+{
+    f3 o, d;
+    float idx, idy, idz;          // reciprocal direction of the (conservative) slab tests
+    uint32_t ng_x, ng_y;          // current node group: base index | hit bits << 24 | imask
+    int sp;
+    float best_t;
+    uint32_t best_prim, best_rank;
+};
+
+template <class Stack>
+ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
+{
+    t.o = o; t.d = d;
+    t.best_t = FLT_MAX; t.best_prim = 0xFFFFFFFFu; t.best_rank = 0xFFFFFFFFu;
+    // exact zeros and denormal-small components are clamped so that 0 * inf never appears
+    const float tiny = 1e-20f;
+    t.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : (f2u(d.x) >> 31 ? -tiny : tiny));
+    t.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : (f2u(d.y) >> 31 ? -tiny : tiny));
+    t.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : (f2u(d.z) >> 31 ? -tiny : tiny));
+    // node group: a root as the single hit child of a virtual parent (imask 0 => relative index 0)
+    t.ng_x = s.main_root; t.ng_y = 0x80000000u;
+    t.sp = 0;
+    if(s.main_root != 0u) { st.put(0, 0u, 0x80000000u); t.sp = 1; }   // sphere tree, visited last
+}
+
+// One step: visit one wide node (if a node group is pending), test the primitives it
+// yielded, pop.  Returns true when the traversal is complete.
+template <bool COUNT, class Stack>
+ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt)
+{
+    const bool nx = t.idx < 0.0f, ny = t.idy < 0.0f, nz = t.idz < 0.0f;
+    const uint32_t octinv = 7u - ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
+    uint32_t tg_x = 0u, tg_y = 0u;        // primitive group
+    if(t.ng_y & 0xFF000000u)
+    {
+        uint32_t bit = msb32(t.ng_y);
+        uint32_t hits_imask = t.ng_y;
+        t.ng_y &= ~(1u << bit);
+        if(t.ng_y & 0xFF000000u)
+        {
+            if(t.sp < ORT_STACK_SIZE) { st.put(t.sp, t.ng_x, t.ng_y); ++t.sp; }
+        }
+        uint32_t slot = (bit - 24u) ^ octinv;
+        uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+        const uint32_t node_index = t.ng_x + rel;
+        const float t_clip = (node_index >= s.main_root) ? t.best_t : FLT_MAX;
+        const q4 *np = s.nodes + 5u * node_index;
+        q4 n0 = ldq(np), n1 = ldq(np + 1), n2 = ldq(np + 2), n3 = ldq(np + 3), n4 = ldq(np + 4);
+        if(COUNT) cnt->node_visits++;
+
+        uint32_t e_imask = f2u(n0.w);
+        float ax = u2f((e_imask & 0xFFu) << 23) * t.idx;
+        float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * t.idy;
+        float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * t.idz;
+        float bx = (n0.x - t.o.x) * t.idx;
+        float by = (n0.y - t.o.y) * t.idy;
+        float bz = (n0.z - t.o.z) * t.idz;
+
+        t.ng_x = f2u(n1.x);
+        tg_x = f2u(n1.y);
+        uint32_t hitmask = 0u;
+        const uint32_t octinv4 = octinv * 0x01010101u;
+#pragma unroll
+        for(int half = 0; half < 2; ++half)
+        {
+            uint32_t meta4 = half ? f2u(n1.w) : f2u(n1.z);
+            uint32_t lox = half ? f2u(n2.y) : f2u(n2.x);
+            uint32_t loy = half ? f2u(n2.w) : f2u(n2.z);
+            uint32_t loz = half ? f2u(n3.y) : f2u(n3.x);
+            uint32_t hix = half ? f2u(n3.w) : f2u(n3.z);
+            uint32_t hiy = half ? f2u(n4.y) : f2u(n4.x);
+            uint32_t hiz = half ? f2u(n4.w) : f2u(n4.z);
+            uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+            uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+            uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+            // per byte: inner children (low 5 bits >= 24, i.e. bits 3 and 4 set) get their slot
+            // XORed with octinv so that the highest hit bit is the nearest child
+            uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
+            uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+            uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+            for(uint32_t k = 0; k < 4; ++k)
+            {
+                float t0x = fmaf(byte_f(nearx, k), ax, bx);
+                float t0y = fmaf(byte_f(neary, k), ay, by);
+                float t0z = fmaf(byte_f(nearz, k), az, bz);
+                float t1x = fmaf(byte_f(farx, k), ax, bx);
+                float t1y = fmaf(byte_f(fary, k), ay, by);
+                float t1z = fmaf(byte_f(farz, k), az, bz);
+                float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
+                if(COUNT) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
+                uint32_t child_bits = (child_bits4 >> (8u * k)) & 0xFFu;
+                uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
+                hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
+            }
+        }
+        t.ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);
+        tg_y = hitmask & 0x00FFFFFFu;
+    }
+    else
+    {
+        tg_x = t.ng_x; tg_y = t.ng_y;
+        t.ng_x = 0u; t.ng_y = 0u;
+    }
+
+    while(tg_y)
+    {
+        uint32_t bit = lsb32(tg_y);
+        tg_y &= tg_y - 1u;
+        uint32_t prim = tg_x + bit, rank, mat;
+        exact::Hit h = intersect_prim(s, prim, t.o, t.d, &rank, &mat);
+        (void)mat;
+        if(COUNT) cnt->shape_tests++;
+        // ray.cpp:653,670,686,708: t >= 1e-6 && t < best; exact ties -> lowest rank
+        if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < t.best_t || (h.t == t.best_t && rank < t.best_rank)))
+        {
+            t.best_t = h.t; t.best_prim = prim; t.best_rank = rank;
+        }
+    }
+
+    if(!(t.ng_y & 0xFF000000u))
+    {
+        if(t.sp == 0) return true;
+        --t.sp;
+        st.get(t.sp, t.ng_x, t.ng_y);
+    }
+    return false;
+}
+
 // Closest hit.  COUNT adds work counters (the counters build of the same code,
 // SURVEY.md 8d).  o/d as in raycast_top_most_node; d need not be unit.
 template <bool COUNT>
 ORT_HD void trace(const SceneView &s, f3 o, f3 d, TraceHit *hit, TraceCounters *cnt)
 {
-    float best_t = FLT_MAX;
-    uint32_t best_prim = 0xFFFFFFFFu, best_rank = 0xFFFFFFFFu;
-
-    // reciprocal direction for the (conservative) slab tests; exact zeros and
-    // denormal-small components are clamped so that 0 * inf never appears
-    const float tiny = 1e-20f;
-    float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : (f2u(d.x) >> 31 ? -tiny : tiny));
-    float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : (f2u(d.y) >> 31 ? -tiny : tiny));
-    float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : (f2u(d.z) >> 31 ? -tiny : tiny));
-    const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
-    const uint32_t octinv = 7u - ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
-
-    uint32_t stack_x[ORT_STACK_SIZE], stack_y[ORT_STACK_SIZE];
-    int sp = 0;
-
-    // node group: a root as the single hit child of a virtual parent (imask 0 => relative index 0)
-    uint32_t ng_x = s.main_root, ng_y = 0x80000000u;
-    if(s.main_root != 0u) { stack_x[0] = 0u; stack_y[0] = 0x80000000u; sp = 1; }   // sphere tree, visited last
-
-    for(;;)
-    {
-        uint32_t tg_x = 0u, tg_y = 0u;        // primitive group
-        if(ng_y & 0xFF000000u)
-        {
-            uint32_t bit = msb32(ng_y);
-            uint32_t hits_imask = ng_y;
-            ng_y &= ~(1u << bit);
-            if(ng_y & 0xFF000000u)
-            {
-                if(sp < ORT_STACK_SIZE) { stack_x[sp] = ng_x; stack_y[sp] = ng_y; ++sp; }
-            }
-            uint32_t slot = (bit - 24u) ^ octinv;
-            uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-            const uint32_t node_index = ng_x + rel;
-            const float t_clip = (node_index >= s.main_root) ? best_t : FLT_MAX;
-            const q4 *np = s.nodes + 5u * node_index;
-            q4 n0 = ldq(np), n1 = ldq(np + 1), n2 = ldq(np + 2), n3 = ldq(np + 3), n4 = ldq(np + 4);
-            if(COUNT) cnt->node_visits++;
-
-            uint32_t e_imask = f2u(n0.w);
-            float ax = u2f((e_imask & 0xFFu) << 23) * idx;
-            float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * idy;
-            float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * idz;
-            float bx = (n0.x - o.x) * idx;
-            float by = (n0.y - o.y) * idy;
-            float bz = (n0.z - o.z) * idz;
-
-            ng_x = f2u(n1.x);
-            tg_x = f2u(n1.y);
-            uint32_t hitmask = 0u;
-            const uint32_t octinv4 = octinv * 0x01010101u;
-#pragma unroll
-            for(int half = 0; half < 2; ++half)
-            {
-                uint32_t meta4 = half ? f2u(n1.w) : f2u(n1.z);
-                uint32_t lox = half ? f2u(n2.y) : f2u(n2.x);
-                uint32_t loy = half ? f2u(n2.w) : f2u(n2.z);
-                uint32_t loz = half ? f2u(n3.y) : f2u(n3.x);
-                uint32_t hix = half ? f2u(n3.w) : f2u(n3.z);
-                uint32_t hiy = half ? f2u(n4.y) : f2u(n4.x);
-                uint32_t hiz = half ? f2u(n4.w) : f2u(n4.z);
-                uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
-                uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
-                uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
-                // per byte: inner children (low 5 bits >= 24, i.e. bits 3 and 4 set) get their slot
-                // XORed with octinv so that the highest hit bit is the nearest child
-                uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
-                uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-                uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#pragma unroll
-                for(uint32_t k = 0; k < 4; ++k)
-                {
-                    float t0x = fmaf(byte_f(nearx, k), ax, bx);
-                    float t0y = fmaf(byte_f(neary, k), ay, by);
-                    float t0z = fmaf(byte_f(nearz, k), az, bz);
-                    float t1x = fmaf(byte_f(farx, k), ax, bx);
-                    float t1y = fmaf(byte_f(fary, k), ay, by);
-                    float t1z = fmaf(byte_f(farz, k), az, bz);
-                    float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-                    float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
-                    if(COUNT) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
-                    uint32_t child_bits = (child_bits4 >> (8u * k)) & 0xFFu;
-                    uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
-                    hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
-                }
-            }
-            ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);
-            tg_y = hitmask & 0x00FFFFFFu;
-        }
-        else
-        {
-            tg_x = ng_x; tg_y = ng_y;
-            ng_x = 0u; ng_y = 0u;
-        }
-
-        while(tg_y)
-        {
-            uint32_t bit = lsb32(tg_y);
-            tg_y &= tg_y - 1u;
-            uint32_t prim = tg_x + bit, rank, mat;
-            exact::Hit h = intersect_prim(s, prim, o, d, &rank, &mat);
-            (void)mat;
-            if(COUNT) cnt->shape_tests++;
-            // ray.cpp:653,670,686,708: t >= 1e-6 && t < best; exact ties -> lowest rank
-            if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < best_t || (h.t == best_t && rank < best_rank)))
-            {
-                best_t = h.t; best_prim = prim; best_rank = rank;
-            }
-        }
-
-        if(!(ng_y & 0xFF000000u))
-        {
-            if(sp == 0) break;
-            --sp;
-            ng_x = stack_x[sp]; ng_y = stack_y[sp];
-        }
-    }
-    hit->t = best_t; hit->prim = best_prim; hit->rank = best_rank;
+    Trav t; LocalStack st;
+    trav_init(s, t, st, o, d);
+    while(!trav_step<COUNT>(s, t, st, cnt)) { }
+    hit->t = t.best_t; hit->prim = t.best_prim; hit->rank = t.best_rank;
 }
 
 // Re-evaluates the winning record to obtain the material and the normalised

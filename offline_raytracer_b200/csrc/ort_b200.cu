@@ -49,10 +49,12 @@ struct OrtScene
     cudaEvent_t ev0, ev1;
     int sm_count;
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
+    int wf_extend_blocks;
     // wavefront path pool
     WfBuffers wf;
     unsigned int *d_active;             // per-iteration "slots still active" counters
     unsigned int *h_active;             // pinned mirror
+    uint32_t *d_sort;                   // hist[512] | cursor[512] | live
 
     SceneView view() const
     {
@@ -154,7 +156,7 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
 {
     if(s->wf.capacity >= capacity) return ORT_OK;
     cudaFree(s->wf.ray_o); cudaFree(s->wf.ray_d); cudaFree(s->wf.hit); cudaFree(s->wf.s_wo);
-    cudaFree(s->wf.s_w); cudaFree(s->wf.s_c); cudaFree(s->wf.s_chunk);
+    cudaFree(s->wf.s_w); cudaFree(s->wf.s_c); cudaFree(s->wf.s_chunk); cudaFree(s->wf.key); cudaFree(s->wf.perm);
     memset(&s->wf, 0, sizeof(s->wf));
     CUDA_TRY(cudaMalloc((void **)&s->wf.ray_o, (size_t)capacity * sizeof(float4)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.ray_d, (size_t)capacity * sizeof(float4)));
@@ -163,9 +165,12 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
     CUDA_TRY(cudaMalloc((void **)&s->wf.s_w, (size_t)capacity * sizeof(float4)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.s_c, (size_t)capacity * sizeof(float4)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.s_chunk, (size_t)capacity * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.key, (size_t)capacity * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.perm, (size_t)capacity * sizeof(uint32_t)));
     s->wf.capacity = capacity;
     if(!s->d_active)
     {
+        CUDA_TRY(cudaMalloc((void **)&s->d_sort, (2 * WF_KEY_BINS + 1) * sizeof(uint32_t)));
         CUDA_TRY(cudaMalloc((void **)&s->d_active, WF_BATCH * sizeof(unsigned int)));
         CUDA_TRY(cudaMallocHost((void **)&s->h_active, WF_BATCH * sizeof(unsigned int)));
     }
@@ -186,21 +191,41 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     WfBuffers wf = s->wf;
     wf.capacity = capacity;
     const unsigned grid = (capacity + 127u) / 128u;
+    const int sorted = getenv("ORT_WF_NOSORT") ? 0 : 1;
+    // persistent EXTEND grid: as many 4-warp blocks as stay resident, each warp owning a slot range
+    if(s->wf_extend_blocks == 0)
+    {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend<false>, 128, 0));
+        s->wf_extend_blocks = (nb > 0 ? nb : 1) * s->sm_count;
+    }
+    unsigned egrid = (unsigned)s->wf_extend_blocks;
+    if(egrid > grid) egrid = grid;
+    const uint32_t warps = egrid * 4u;
+    const uint32_t slots_per_warp = ((capacity + warps - 1u) / warps + 31u) & ~31u;
+    uint32_t *hist = s->d_sort, *cursor = s->d_sort + WF_KEY_BINS, *live = s->d_sort + 2 * WF_KEY_BINS;
     k_wf_reset<<<grid, 128, 0, stream>>>(wf);
     CUDA_TRY(cudaMemsetAsync(s->d_active, 0, WF_BATCH * sizeof(unsigned int), stream));
-    k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active);
+    k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active, live, 0);
     *launches += 2;
     for(;;)
     {
         CUDA_TRY(cudaMemsetAsync(s->d_active, 0, WF_BATCH * sizeof(unsigned int), stream));
         for(int it = 0; it < WF_BATCH; ++it)
         {
+            CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), stream));
 #ifdef ORT_COUNTERS
-            k_wf_extend<true><<<grid, 128, 0, stream>>>(a.scene, wf, a.stats);
+            k_wf_extend<true><<<egrid, 128, 0, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
 #else
-            k_wf_extend<false><<<grid, 128, 0, stream>>>(a.scene, wf, a.stats);
+            k_wf_extend<false><<<egrid, 128, 0, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
 #endif
-            k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active + it);
+            if(sorted)
+            {
+                k_wf_scan<<<1, WF_KEY_BINS, 0, stream>>>(hist, cursor, live);
+                k_wf_scatter<<<(capacity + 1023u) / 1024u, 1024, 0, stream>>>(wf, cursor);
+                *launches += 2;
+            }
+            k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active + it, live, sorted);
         }
         *launches += 2 * WF_BATCH;
         CUDA_TRY(cudaGetLastError());
@@ -374,6 +399,7 @@ int ort_scene_destroy(OrtScene *s)
     cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb);
     cudaFree(s->wf.ray_o); cudaFree(s->wf.ray_d); cudaFree(s->wf.hit); cudaFree(s->wf.s_wo);
     cudaFree(s->wf.s_w); cudaFree(s->wf.s_c); cudaFree(s->wf.s_chunk); cudaFree(s->d_active);
+    cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->d_sort);
     if(s->h_active) cudaFreeHost(s->h_active);
     if(s->ev0) cudaEventDestroy(s->ev0);
     if(s->ev1) cudaEventDestroy(s->ev1);

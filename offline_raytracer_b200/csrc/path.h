@@ -30,6 +30,17 @@ namespace ort {
 
 #define ORT_EULER 2.71828182845904523536028747135266249f   // ray.cpp:4
 
+// Out-of-line building blocks: the BSDF code calls these many times (normalize x12,
+// geometry x4, ggx_distribution x3, ...); inlining every copy makes SHADE ~77 KB of SASS,
+// more than the instruction caches hold (ncu: icc hit rate 63 %, "no_instruction" the top
+// stall).  One shared copy each keeps the kernel resident.
+#if defined(__CUDA_ARCH__) && !defined(ORT_SHADE_INLINE_ALL)
+#define ORT_HD_BIG __device__ __noinline__
+#else
+#define ORT_HD_BIG ORT_HD
+#endif
+ORT_HD_BIG f3 nrm(f3 a) { return normalize(a); }
+
 // ---- RNG -------------------------------------------------------------------
 ORT_HD void xor_shift_32(uint32_t *s)                                    // random.h:5-16
 {
@@ -125,12 +136,12 @@ ORT_HD float pow4_ref(float x) { return powf(x, 4.0f); }
 ORT_HD float exp_ref(float y) { return powf(ORT_EULER, y); }
 #endif
 
-ORT_HD f3 fresnel(f3 Ks, float l_dot_h)                                  // ray.cpp:825-831
+ORT_HD_BIG f3 fresnel(f3 Ks, float l_dot_h)                                  // ray.cpp:825-831
 {
     return Ks + (1 - pow5_ref(1.0f - absolute(l_dot_h))) * (mk3(1.0f, 1.0f, 1.0f) - Ks);
 }
 
-ORT_HD float ggx_distribution(f3 N, f3 H, float roughness)               // ray.cpp:834-865
+ORT_HD_BIG float ggx_distribution(f3 N, f3 H, float roughness)               // ray.cpp:834-865
 {
     float result = 0.0f;
     float n_dot_h = dot(N, H);
@@ -145,7 +156,7 @@ ORT_HD float ggx_distribution(f3 N, f3 H, float roughness)               // ray.
     return result;
 }
 
-ORT_HD float geometry(f3 w, f3 N, f3 m, float roughness)                 // ray.cpp:868-897
+ORT_HD_BIG float geometry(f3 w, f3 N, f3 m, float roughness)                 // ray.cpp:868-897
 {
     float result = 0.0f;
     float w_dot_n = dot(w, N);
@@ -184,7 +195,7 @@ ORT_HD Beern get_beer_n(f3 N, f3 wo, float ior)                          // ray.
 ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, f3 Kd, f3 Ks, f3 Kt, float ior, float roughness, float distance)   // ray.cpp:936-1005
 {
     f3 Ed = Kd / ORT_PI_32;
-    f3 H = ref_sign(dot(wi, N)) * normalize(wo + wi);
+    f3 H = ref_sign(dot(wi, N)) * nrm(wo + wi);
     float wi_dot_h = dot(wi, H);
     f3 Es = mk3(0.0f, 0.0f, 0.0f);
     float wi_dot_n = dot(wi, N);
@@ -207,7 +218,7 @@ ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, f3 Kd, f3 Ks, f3 Kt, float ior, fl
             At.z = exp_ref(distance * logf(Kt.z));
         }
         Beern bn = get_beer_n(N, wo, ior);
-        f3 m = normalize(-(bn.ni * wi + bn.no * wo));
+        f3 m = nrm(-(bn.ni * wi + bn.no * wo));
         float r = get_radicand(m, wo, bn.n);
         if(r < 0.0f)
         {
@@ -237,7 +248,7 @@ ORT_HD float pdf_brdf(f3 N, f3 wi, f3 wo, float roughness, f3 Kd, f3 Ks, f3 Kt, 
     float s = Kd_l + Ks_l + Kt_l;
     float pd_c = Kd_l / s, ps_c = Ks_l / s, pt_c = Kt_l / s;
     float pd = absolute(dot(wi, N)) / ORT_PI_32;
-    f3 H = ref_sign(dot(N, wi)) * normalize(wo + wi);
+    f3 H = ref_sign(dot(N, wi)) * nrm(wo + wi);
     float n_dot_h = dot(N, H);
     float wi_dot_h = dot(wi, H);
     float ps = 0.0f;
@@ -251,7 +262,7 @@ ORT_HD float pdf_brdf(f3 N, f3 wi, f3 wo, float roughness, f3 Kd, f3 Ks, f3 Kt, 
         }
     }
     Beern bn = get_beer_n(N, wo, ior);
-    f3 m = normalize(-(bn.ni * wi + bn.no * wo));
+    f3 m = nrm(-(bn.ni * wi + bn.no * wo));
     float r = get_radicand(m, wo, bn.n);
     float pt = ps;                                                       // sic, ray.cpp:1046
     if(pt_c > 0.0f && r >= 0.0f)
@@ -269,14 +280,14 @@ ORT_HD float pdf_brdf(f3 N, f3 wi, f3 wo, float roughness, f3 Kd, f3 Ks, f3 Kt, 
     return pd_c * pd + ps_c * ps + pt_c * pt;
 }
 
-ORT_HD f3 sample_lobe(f3 N, float c, float phi)                          // ray.cpp:1065-1091
+ORT_HD_BIG f3 sample_lobe(f3 N, float c, float phi)                          // ray.cpp:1065-1091
 {
-    N = normalize(N);
+    N = nrm(N);
     float s = sqrtf(1.0f - c * c);
     f3 K = mk3(s * cosf(phi), s * sinf(phi), c);
     if(absolute(N.z - 1.0f) < 0.0001f) return K;
     if(absolute(N.z + 1.0f) < 0.0001f) return mk3(K.x, -K.y, -K.z);
-    f3 B = normalize(mk3(-N.y, N.x, 0.0f));
+    f3 B = nrm(mk3(-N.y, N.x, 0.0f));
     f3 C = cross(N, B);
     return K.x * B + K.y * C + K.z * N;
 }
@@ -314,7 +325,7 @@ ORT_HD SampleBRDF sample_brdf(uint32_t *series, f3 N, f3 wo, float roughness, f3
         }
         if(reflect) res.wi = 2.0f * absolute(dot(wo, m)) * m - wo;
     }
-    res.wi = normalize(res.wi);
+    res.wi = nrm(res.wi);
     return res;
 }
 
@@ -334,7 +345,7 @@ ORT_HD f3 pixel_focal_point(const PathConsts &c, int x, int y)
 {
     float pixel_x = (2.0f * x / (float)c.width) - 1.0f;
     float pixel_y = (2.0f * y / (float)c.height) - 1.0f;
-    f3 camera_to_pixel = normalize(pixel_x * c.cam_x + pixel_y * c.cam_y - c.cam_z);
+    f3 camera_to_pixel = nrm(pixel_x * c.cam_x + pixel_y * c.cam_y - c.cam_z);
     return c.cam_p + c.focal_length * camera_to_pixel;
 }
 
@@ -344,8 +355,8 @@ ORT_HD void generate_primary(const PathConsts &c, f3 focal_point, Path *p)
     float random_rad = random_between(&p->series, 0.0f, 2 * ORT_PI_32);
     f3 lens = c.cam_p + c.aperture_radius * cosf(random_rad) * c.cam_x
                       + c.aperture_radius * sinf(random_rad) * c.cam_y - c.lens_z_offset * c.cam_z;
-    p->dir = normalize(focal_point - lens);
-    p->wo = -normalize(p->dir);          // normalised twice, as ray.cpp:1237,1240
+    p->dir = nrm(focal_point - lens);
+    p->wo = -nrm(p->dir);          // normalised twice, as ray.cpp:1237,1240
     p->origin = lens;
     p->weight = mk3(1.0f, 1.0f, 1.0f);
     p->normal = mk3(0.0f, 0.0f, 0.0f);

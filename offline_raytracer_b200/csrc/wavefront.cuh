@@ -20,7 +20,7 @@
 //
 // Slot state, structure-of-arrays, 16-byte records (one 128-bit access each):
 //   ray_o   origin.xyz | state word (low 2 bits: DEAD/ACTIVE/FRESH)
-//   ray_d   direction.xyz | -
+//   ray_d   direction.xyz | 1 if the ray is a primary
 //   hit     t | primitive index                                   (8 bytes)
 //   s_wo    wo.xyz | xorshift state of the stream
 //   s_w     throughput weight.xyz | pixel index
@@ -40,6 +40,8 @@ struct WfBuffers
     uint2 *hit;
     float4 *s_wo, *s_w, *s_c;
     uint32_t *s_chunk;
+    uint32_t *key;       // shading key written by EXTEND: primary << 8 | min(material, 255); 511 = dead
+    uint32_t *perm;      // slots grouped by key (counting sort)
     uint32_t capacity;
 };
 
@@ -49,28 +51,96 @@ __global__ void k_wf_reset(WfBuffers wf)
     if(i < wf.capacity) wf.ray_o[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_FRESH));
 }
 
+// shared-memory traversal stack: entry k of thread t lives at column t of row k, so the 32
+// lanes of a warp touch 32 consecutive 8-byte words (no bank conflicts) and the stack never
+// competes with BVH nodes for L1 lines
+struct SharedStack
+{
+    uint2 *col;      // &smem[threadIdx.x]
+    __device__ __forceinline__ void put(int i, uint32_t a, uint32_t b) { col[i * 128] = make_uint2(a, b); }
+    __device__ __forceinline__ void get(int i, uint32_t &a, uint32_t &b) const { uint2 v = col[i * 128]; a = v.x; b = v.y; }
+};
+
+#define WF_KEY_DEAD 511u
+#define WF_KEY_BINS 512u
+
+// EXTEND.  Persistent warps: each warp owns a contiguous range of slots and keeps its 32 lanes
+// busy by handing the next rays of the range to lanes whose traversal has finished (dynamic
+// fetch), instead of letting them idle until the slowest ray of a fixed batch of 32 is done --
+// ncu: 8.5 of 32 lanes active without it.  Lanes then advance in lock step, one wide-node visit
+// per trip.  Also emits the slot's shading key (primary flag, material of the hit) and counts it,
+// for the counting sort that groups SHADE by material.
 template <bool COUNT>
 __global__ void __launch_bounds__(128)
-k_wf_extend(SceneView scene, WfBuffers wf, unsigned long long *stats)
+k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned long long *stats, uint32_t *hist)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint2 smem_stack[ORT_STACK_SIZE * 128];
+    __shared__ uint32_t sh_hist[WF_KEY_BINS];
+    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh_hist[k] = 0u;
+    __syncthreads();
+    SharedStack st; st.col = smem_stack + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long range_lo = (unsigned long long)warp * slots_per_warp;
+    uint32_t next = (uint32_t)(range_lo < wf.capacity ? range_lo : wf.capacity);
+    unsigned long long range_hi_l = range_lo + slots_per_warp;
+    const uint32_t end = (uint32_t)(range_hi_l < wf.capacity ? range_hi_l : wf.capacity);
+
+    Trav t;
+    t.ng_x = t.ng_y = 0u; t.sp = 0;
+    bool has_ray = false;
+    uint32_t slot = 0u, is_primary = 0u;
     unsigned long long nodes = 0, boxes = 0, shapes = 0, rays = 0;
-    if(i < wf.capacity)
+
+    for(;;)
     {
-        float4 ro = wf.ray_o[i];
-        if(__float_as_uint(ro.w) == WF_ACTIVE)
+        uint32_t idle_mask = __ballot_sync(0xFFFFFFFFu, !has_ray);
+        if(idle_mask != 0u && next < end)
         {
-            float4 rd = wf.ray_d[i];
-            TraceHit hit; TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
-            trace<COUNT>(scene, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), &hit, &cnt);
-            wf.hit[i] = make_uint2(__float_as_uint(hit.t), hit.prim);
-            rays = 1;
-            if(COUNT) { nodes = cnt.node_visits; boxes = cnt.box_tests; shapes = cnt.shape_tests; }
+            // hand consecutive slots of the range to the idle lanes
+            uint32_t my = next + __popc(idle_mask & ((1u << lane) - 1u));
+            if(!has_ray && my < end)
+            {
+                float4 ro = wf.ray_o[my];
+                if(__float_as_uint(ro.w) == WF_ACTIVE)
+                {
+                    float4 rd = wf.ray_d[my];
+                    trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
+                    is_primary = __float_as_uint(rd.w);
+                    slot = my;
+                    has_ray = true;
+                    ++rays;
+                }
+                else { wf.key[my] = WF_KEY_DEAD; atomicAdd(&sh_hist[WF_KEY_DEAD], 1u); }
+            }
+            next += __popc(idle_mask);
+            if(next > end) next = end;
+        }
+        if(__ballot_sync(0xFFFFFFFFu, has_ray) == 0u)
+        {
+            if(next >= end) break;
+            continue;
+        }
+        if(has_ray)
+        {
+            TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
+            bool done = trav_step<COUNT>(scene, t, st, &cnt);
+            if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; shapes += cnt.shape_tests; }
+            if(done)
+            {
+                wf.hit[slot] = make_uint2(__float_as_uint(t.best_t), t.best_prim);
+                uint32_t mat = 0u;
+                if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
+                uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
+                wf.key[slot] = key;
+                atomicAdd(&sh_hist[key], 1u);
+                has_ray = false;
+            }
         }
     }
     rays = warp_sum(rays);
     if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); shapes = warp_sum(shapes); }
-    if((threadIdx.x & 31) == 0 && rays)
+    if(lane == 0 && rays)
     {
         atomicAdd(&stats[STAT_RAYS], rays);
         if(COUNT)
@@ -80,6 +150,68 @@ k_wf_extend(SceneView scene, WfBuffers wf, unsigned long long *stats)
             atomicAdd(&stats[STAT_SHAPE_TESTS], shapes);
         }
     }
+    // the block's share of the key histogram (first pass of the counting sort)
+    __syncthreads();
+    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) if(sh_hist[k]) atomicAdd(&hist[k], sh_hist[k]);
+}
+
+// ---- counting sort of the slots by shading key -------------------------------------------
+// hist[k] = number of slots with key k; offsets = exclusive scan; perm = slots grouped by key.
+__global__ void __launch_bounds__(256)
+k_wf_hist(WfBuffers wf, uint32_t *hist)
+{
+    __shared__ uint32_t sh[WF_KEY_BINS];
+    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh[k] = 0u;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.capacity; i += stride) atomicAdd(&sh[wf.key[i]], 1u);
+    __syncthreads();
+    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) if(sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+
+// one block: exclusive scan of the 512 bins into cursor[], and live = slots that are not dead
+__global__ void __launch_bounds__(512)
+k_wf_scan(const uint32_t *hist, uint32_t *cursor, uint32_t *live)
+{
+    __shared__ uint32_t sh[WF_KEY_BINS];
+    uint32_t v = hist[threadIdx.x];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for(uint32_t o = 1; o < WF_KEY_BINS; o <<= 1)
+    {
+        uint32_t add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    cursor[threadIdx.x] = sh[threadIdx.x] - v;
+    if(threadIdx.x == WF_KEY_DEAD) *live = sh[threadIdx.x] - v;     // everything before the dead bin
+}
+
+// Two-level append: lanes of a warp with the same key are ranked with one match_any, warps of a
+// block reserve their ranges in shared-memory counters, and the block then reserves its range of
+// each key with ONE global atomic per key present -- a handful per 1024 slots instead of one per
+// warp (ncu: the per-warp version spent 58 us per pass serialised on a few hot counters).
+__global__ void __launch_bounds__(1024)
+k_wf_scatter(WfBuffers wf, uint32_t *cursor)
+{
+    __shared__ uint32_t cnt[WF_KEY_BINS], base[WF_KEY_BINS];
+    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) cnt[k] = 0u;
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < wf.capacity;
+    uint32_t key = valid ? wf.key[i] : WF_KEY_BINS;      // padding threads: a key of their own, never counted
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    uint32_t leader = __ffs(peers) - 1u;
+    uint32_t lane = threadIdx.x & 31u;
+    uint32_t local = 0u;
+    if(lane == leader && valid) local = atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+    local = __shfl_sync(0xFFFFFFFFu, local, leader) + __popc(peers & ((1u << lane) - 1u));
+    __syncthreads();
+    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x)
+        if(cnt[k]) base[k] = atomicAdd(&cursor[k], cnt[k]);
+    __syncthreads();
+    if(valid) wf.perm[base[key] + local] = i;
 }
 
 // material + normalised normal of the winning record (ray.cpp:817).  Triangles -- almost all
@@ -100,13 +232,22 @@ __device__ __forceinline__ void wf_finish_hit(const SceneView &s, uint32_t prim,
     finish_hit(s, h, o, d, mat, normal);
 }
 
+// `sorted`: thread j handles slot perm[j] for j < *live (slots grouped by material, so the lanes
+// of a warp mostly take the same branches of the BSDF code); else thread j handles slot j.
 __global__ void __launch_bounds__(128)
-k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out)
+k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uint32_t *live, int sorted)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n_samples = 0;
     unsigned int still_active = 0;
-    if(i < wf.capacity)
+    uint32_t i = j;
+    bool in_range = j < wf.capacity;
+    if(sorted)
+    {
+        in_range = j < *live;
+        if(in_range) i = wf.perm[j];
+    }
+    if(in_range)
     {
         float4 ro = wf.ray_o[i];
         uint32_t state = __float_as_uint(ro.w);
@@ -206,7 +347,7 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out)
             if(have_ray)
             {
                 wf.ray_o[i] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
-                wf.ray_d[i] = make_float4(p.dir.x, p.dir.y, p.dir.z, 0.f);
+                wf.ray_d[i] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(primary_next ? 1u : 0u));
                 wf.s_wo[i] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
                 wf.s_w[i] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
                 wf.s_c[i] = make_float4(color.x, color.y, color.z,

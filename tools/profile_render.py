@@ -16,9 +16,10 @@ ap.add_argument("--spp", type=int, default=32)
 ap.add_argument("--chunk", type=int, default=16)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--kernel", type=int, default=0)
+ap.add_argument("--lib", default="")
 a = ap.parse_args()
 hs = ort.HostScene.load(a.scene, a.base, a.width, a.height)
-sc = ort.Scene(hs.world, hs.root, 0)
+sc = ort.Scene(hs.world, hs.root, 0, library=ort.lib(os.path.abspath(a.lib)) if a.lib else None)
 P = ort.default_params(a.width, a.height, a.spp, chunk_spp=a.chunk, kernel=a.kernel)
 for _ in range(a.reps):
     img, st = sc.render(hs.camera, P)
