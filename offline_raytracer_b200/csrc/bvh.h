@@ -124,7 +124,7 @@ ORT_HD f3 q3(q4 v) { return mk3(v.x, v.y, v.z); }
 
 // exact intersection of one record (dispatch on kind); returns t (-1 = miss) and
 // the UNNORMALISED normal, as the reference's intersectors do.
-ORT_HD exact::Hit intersect_prim(const SceneView &s, uint32_t prim, f3 o, f3 d, uint32_t *rank, uint32_t *mat)
+ORT_HD exact::Hit intersect_prim(const SceneView &s, uint32_t prim, f3 o, f3 d, f3 inv, uint32_t *rank, uint32_t *mat)
 {
     const q4 *p = s.prims + 3u * prim;
     q4 A = ldq(p), B = ldq(p + 1), C = ldq(p + 2);
@@ -132,7 +132,7 @@ ORT_HD exact::Hit intersect_prim(const SceneView &s, uint32_t prim, f3 o, f3 d, 
     *mat = f2u(B.w);
     uint32_t kind = f2u(C.w);
     if((kind & 0xFFu) == PRIM_TRIANGLE) return exact::triangle(q3(A), q3(B), q3(C), o, d);
-    if((kind & 0xFFu) == PRIM_AAB) return exact::aab(q3(A), q3(B), o, d);
+    if((kind & 0xFFu) == PRIM_AAB) return exact::aab_inv(q3(A), q3(B), o, inv);
     if((kind & 0xFFu) == PRIM_SPHERE) { int inner; return exact::sphere(q3(A), B.x, o, d, &inner); }
     const q4 *c = s.cyl + 4u * (kind >> 8);
     q4 c0 = ldq(c), c1 = ldq(c + 1), c2 = ldq(c + 2), c3 = ldq(c + 3);
@@ -165,7 +165,7 @@ struct LocalStack
 struct Trav
 {
     f3 o, d;
-    float idx, idy, idz;          // reciprocal direction of the (conservative) slab tests
+    f3 inv;                       // (1/d.x, 1/d.y, 1/d.z), IEEE, as ray.cpp:210 forms it for box shapes
     uint32_t ng_x, ng_y;          // current node group: base index | hit bits << 24 | imask
     int sp;
     float best_t;
@@ -177,11 +177,7 @@ ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
 {
     t.o = o; t.d = d;
     t.best_t = FLT_MAX; t.best_prim = 0xFFFFFFFFu; t.best_rank = 0xFFFFFFFFu;
-    // exact zeros and denormal-small components are clamped so that 0 * inf never appears
-    const float tiny = 1e-20f;
-    t.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : (f2u(d.x) >> 31 ? -tiny : tiny));
-    t.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : (f2u(d.y) >> 31 ? -tiny : tiny));
-    t.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : (f2u(d.z) >> 31 ? -tiny : tiny));
+    t.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     // node group: a root as the single hit child of a virtual parent (imask 0 => relative index 0)
     t.ng_x = s.main_root; t.ng_y = 0x80000000u;
     t.sp = 0;
@@ -193,7 +189,13 @@ ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
 template <bool COUNT, class Stack>
 ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt)
 {
-    const bool nx = t.idx < 0.0f, ny = t.idy < 0.0f, nz = t.idz < 0.0f;
+    // reciprocal direction of the (conservative) slab tests: the exact one, except that zero and
+    // denormal-small components are clamped so that 0 * inf never appears
+    const float tiny = 1e-20f, huge = 1e20f;
+    const float idx = fabsf(t.d.x) > tiny ? t.inv.x : (f2u(t.d.x) >> 31 ? -huge : huge);
+    const float idy = fabsf(t.d.y) > tiny ? t.inv.y : (f2u(t.d.y) >> 31 ? -huge : huge);
+    const float idz = fabsf(t.d.z) > tiny ? t.inv.z : (f2u(t.d.z) >> 31 ? -huge : huge);
+    const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
     const uint32_t octinv = 7u - ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
     uint32_t tg_x = 0u, tg_y = 0u;        // primitive group
     if(t.ng_y & 0xFF000000u)
@@ -214,12 +216,12 @@ ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt
         if(COUNT) cnt->node_visits++;
 
         uint32_t e_imask = f2u(n0.w);
-        float ax = u2f((e_imask & 0xFFu) << 23) * t.idx;
-        float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * t.idy;
-        float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * t.idz;
-        float bx = (n0.x - t.o.x) * t.idx;
-        float by = (n0.y - t.o.y) * t.idy;
-        float bz = (n0.z - t.o.z) * t.idz;
+        float ax = u2f((e_imask & 0xFFu) << 23) * idx;
+        float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * idy;
+        float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * idz;
+        float bx = (n0.x - t.o.x) * idx;
+        float by = (n0.y - t.o.y) * idy;
+        float bz = (n0.z - t.o.z) * idz;
 
         t.ng_x = f2u(n1.x);
         tg_x = f2u(n1.y);
@@ -275,7 +277,7 @@ ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt
         uint32_t bit = lsb32(tg_y);
         tg_y &= tg_y - 1u;
         uint32_t prim = tg_x + bit, rank, mat;
-        exact::Hit h = intersect_prim(s, prim, t.o, t.d, &rank, &mat);
+        exact::Hit h = intersect_prim(s, prim, t.o, t.d, t.inv, &rank, &mat);
         (void)mat;
         if(COUNT) cnt->shape_tests++;
         // ray.cpp:653,670,686,708: t >= 1e-6 && t < best; exact ties -> lowest rank
@@ -317,7 +319,7 @@ ORT_HD void finish_hit(const SceneView &s, const TraceHit &hit, f3 o, f3 d, uint
         return;
     }
     uint32_t rank;
-    exact::Hit h = intersect_prim(s, hit.prim, o, d, &rank, mat);
+    exact::Hit h = intersect_prim(s, hit.prim, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), &rank, mat);
     *normal = normalize(h.n);
 }
 

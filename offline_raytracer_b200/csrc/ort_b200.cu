@@ -50,6 +50,7 @@ struct OrtScene
     int sm_count;
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
     int wf_extend_blocks;
+    uint32_t stack_rows;                // wide-tree depth + 1: rows of the shared-memory traversal stack
     // wavefront path pool
     WfBuffers wf;
     unsigned int *d_active;             // per-iteration "slots still active" counters
@@ -192,11 +193,12 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     wf.capacity = capacity;
     const unsigned grid = (capacity + 127u) / 128u;
     const int sorted = getenv("ORT_WF_NOSORT") ? 0 : 1;
+    const size_t stack_bytes = (size_t)s->stack_rows * 128 * sizeof(uint2);
     // persistent EXTEND grid: as many 4-warp blocks as stay resident, each warp owning a slot range
     if(s->wf_extend_blocks == 0)
     {
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend<false>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend<false>, 128, s->stack_rows * 128 * sizeof(uint2)));
         s->wf_extend_blocks = (nb > 0 ? nb : 1) * s->sm_count;
     }
     unsigned egrid = (unsigned)s->wf_extend_blocks;
@@ -215,9 +217,9 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         {
             CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), stream));
 #ifdef ORT_COUNTERS
-            k_wf_extend<true><<<egrid, 128, 0, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+            k_wf_extend<true><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
 #else
-            k_wf_extend<false><<<egrid, 128, 0, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+            k_wf_extend<false><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
 #endif
             if(sorted)
             {
@@ -367,6 +369,7 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     s->device = device;
     s->info = flat.info;
     s->main_root = flat.main_root;
+    s->stack_rows = flat.wide_depth + 1u;
     s->node_count = (uint32_t)flat.nodes.size();
     s->prim_count = (uint32_t)flat.prims.size();
     s->light_count = (uint32_t)flat.light_is_sphere.size();

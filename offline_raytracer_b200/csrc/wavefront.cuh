@@ -56,7 +56,7 @@ __global__ void k_wf_reset(WfBuffers wf)
 // competes with BVH nodes for L1 lines
 struct SharedStack
 {
-    uint2 *col;      // &smem[threadIdx.x]
+    uint2 *col;      // &smem[threadIdx.x]; rows of 128 threads
     __device__ __forceinline__ void put(int i, uint32_t a, uint32_t b) { col[i * 128] = make_uint2(a, b); }
     __device__ __forceinline__ void get(int i, uint32_t &a, uint32_t &b) const { uint2 v = col[i * 128]; a = v.x; b = v.y; }
 };
@@ -70,11 +70,21 @@ struct SharedStack
 // ncu: 8.5 of 32 lanes active without it.  Lanes then advance in lock step, one wide-node visit
 // per trip.  Also emits the slot's shading key (primary flag, material of the hit) and counts it,
 // for the counting sort that groups SHADE by material.
+// resident 4-warp blocks per SM the register allocation must allow (measured on B200, 1080p:
+// extend 8 / shade 6 = 116 ms; 6/6 = 119 ms; unconstrained (96 / 89 registers) = 127 ms)
+#ifndef ORT_EXTEND_MIN_BLOCKS
+#define ORT_EXTEND_MIN_BLOCKS 8
+#endif
+#ifndef ORT_SHADE_MIN_BLOCKS
+#define ORT_SHADE_MIN_BLOCKS 6
+#endif
+// dynamic shared memory: (wide-tree depth + 1) stack rows of 128 uint2 -- sized per scene, so a
+// shallow tree does not pay for ORT_STACK_SIZE rows of occupancy
 template <bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
 k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned long long *stats, uint32_t *hist)
 {
-    __shared__ uint2 smem_stack[ORT_STACK_SIZE * 128];
+    extern __shared__ uint2 smem_stack[];
     __shared__ uint32_t sh_hist[WF_KEY_BINS];
     for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh_hist[k] = 0u;
     __syncthreads();
@@ -234,7 +244,7 @@ __device__ __forceinline__ void wf_finish_hit(const SceneView &s, uint32_t prim,
 
 // `sorted`: thread j handles slot perm[j] for j < *live (slots grouped by material, so the lanes
 // of a warp mostly take the same branches of the BSDF code); else thread j handles slot j.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, ORT_SHADE_MIN_BLOCKS)
 k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uint32_t *live, int sorted)
 {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
