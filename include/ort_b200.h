@@ -157,6 +157,10 @@ typedef struct OrtRenderStats
     uint64_t shape_tests;      /* primitive tests        (counters build only, else 0) */
     float    device_ms;        /* CUDA-event time of the kernels of this call */
     uint32_t kernel_launches;  /* kernels launched by this call */
+    float    extend_ms;        /* wavefront: summed CUDA-event time of the EXTEND launches */
+    float    shade_ms;         /* wavefront: ... of the SHADE launches */
+    float    sort_ms;          /* wavefront: ... of the key scan + scatter launches */
+    uint32_t reserved;
 } OrtRenderStats;
 
 void ort_render_params_default(OrtRenderParams *params, int32_t width, int32_t height,

@@ -51,6 +51,9 @@ struct OrtScene
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
     int wf_extend_blocks;
     uint32_t stack_rows;                // wide-tree depth + 1: rows of the shared-memory traversal stack
+    int wf_events_ready;
+    cudaEvent_t wf_done[2], wf_ev[2][8][4];
+    float extend_ms, shade_ms, sort_ms; // summed stage times of the last wavefront render
     // wavefront path pool
     WfBuffers wf;
     unsigned int *d_active;             // per-iteration "slots still active" counters
@@ -156,24 +159,17 @@ PathConsts make_consts(const OrtScene *s, const OrtCamera *cam, const OrtRenderP
 int ensure_wavefront(OrtScene *s, uint32_t capacity)
 {
     if(s->wf.capacity >= capacity) return ORT_OK;
-    cudaFree(s->wf.ray_o); cudaFree(s->wf.ray_d); cudaFree(s->wf.hit); cudaFree(s->wf.s_wo);
-    cudaFree(s->wf.s_w); cudaFree(s->wf.s_c); cudaFree(s->wf.s_chunk); cudaFree(s->wf.key); cudaFree(s->wf.perm);
+    cudaFree(s->wf.rec); cudaFree(s->wf.key); cudaFree(s->wf.perm);
     memset(&s->wf, 0, sizeof(s->wf));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.ray_o, (size_t)capacity * sizeof(float4)));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.ray_d, (size_t)capacity * sizeof(float4)));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.hit, (size_t)capacity * sizeof(uint2)));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.s_wo, (size_t)capacity * sizeof(float4)));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.s_w, (size_t)capacity * sizeof(float4)));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.s_c, (size_t)capacity * sizeof(float4)));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.s_chunk, (size_t)capacity * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.rec, (size_t)capacity * WF_REC_QUADS * sizeof(float4)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.key, (size_t)capacity * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.perm, (size_t)capacity * sizeof(uint32_t)));
     s->wf.capacity = capacity;
     if(!s->d_active)
     {
         CUDA_TRY(cudaMalloc((void **)&s->d_sort, (2 * WF_KEY_BINS + 1) * sizeof(uint32_t)));
-        CUDA_TRY(cudaMalloc((void **)&s->d_active, WF_BATCH * sizeof(unsigned int)));
-        CUDA_TRY(cudaMallocHost((void **)&s->h_active, WF_BATCH * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc((void **)&s->d_active, 2 * WF_BATCH * sizeof(unsigned int)));
+        CUDA_TRY(cudaMallocHost((void **)&s->h_active, 2 * WF_BATCH * sizeof(unsigned int)));
     }
     return ORT_OK;
 }
@@ -183,7 +179,7 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
 // iterations, so the host never waits on a single launch.
 int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint32_t *launches)
 {
-    uint32_t capacity = 1u << 21;
+    uint32_t capacity = 1u << 22;      // 4 Mi slots x 104 B = 416 MB (measured: 1 Mi 636, 2 Mi 707, 4 Mi 720 Msamples/s at 1080p)
     if(const char *e = getenv("ORT_WF_SLOTS")) { long v = atol(e); if(v >= 1024 && v <= (1l << 26)) capacity = (uint32_t)v; }
     unsigned long long items128 = (a.total_items + 127ull) & ~127ull;
     if(items128 < capacity) capacity = (uint32_t)items128;
@@ -206,34 +202,89 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     const uint32_t warps = egrid * 4u;
     const uint32_t slots_per_warp = ((capacity + warps - 1u) / warps + 31u) & ~31u;
     uint32_t *hist = s->d_sort, *cursor = s->d_sort + WF_KEY_BINS, *live = s->d_sort + 2 * WF_KEY_BINS;
+    if(!s->wf_events_ready)
+    {
+        for(int b = 0; b < 2; ++b)
+        {
+            CUDA_TRY(cudaEventCreate(&s->wf_done[b]));
+            for(int it = 0; it < WF_BATCH; ++it)
+                for(int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreate(&s->wf_ev[b][it][k]));
+        }
+        s->wf_events_ready = 1;
+    }
+    s->extend_ms = s->shade_ms = s->sort_ms = 0.f;
     k_wf_reset<<<grid, 128, 0, stream>>>(wf);
-    CUDA_TRY(cudaMemsetAsync(s->d_active, 0, WF_BATCH * sizeof(unsigned int), stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_active, 0, 2 * WF_BATCH * sizeof(unsigned int), stream));
     k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active, live, 0);
     *launches += 2;
-    for(;;)
+    // Batches of WF_BATCH iterations are enqueued one ahead of the read-back of the previous
+    // batch's "still active" counters, so the device never drains while the host decides.
+    const bool pipelined = a.total_items > 4ull * capacity;
+    auto enqueue = [&](int b) -> int
     {
-        CUDA_TRY(cudaMemsetAsync(s->d_active, 0, WF_BATCH * sizeof(unsigned int), stream));
+        unsigned int *act = s->d_active + b * WF_BATCH;
+        CUDA_TRY(cudaMemsetAsync(act, 0, WF_BATCH * sizeof(unsigned int), stream));
         for(int it = 0; it < WF_BATCH; ++it)
         {
             CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), stream));
+            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][0], stream));
 #ifdef ORT_COUNTERS
             k_wf_extend<true><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
 #else
             k_wf_extend<false><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
 #endif
+            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][1], stream));
             if(sorted)
             {
                 k_wf_scan<<<1, WF_KEY_BINS, 0, stream>>>(hist, cursor, live);
                 k_wf_scatter<<<(capacity + 1023u) / 1024u, 1024, 0, stream>>>(wf, cursor);
                 *launches += 2;
             }
-            k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active + it, live, sorted);
+            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][2], stream));
+            k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, act + it, live, sorted);
+            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][3], stream));
         }
         *launches += 2 * WF_BATCH;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(s->h_active, s->d_active, WF_BATCH * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        if(s->h_active[WF_BATCH - 1] == 0) break;
+        CUDA_TRY(cudaMemcpyAsync(s->h_active + b * WF_BATCH, act, WF_BATCH * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaEventRecord(s->wf_done[b], stream));
+        return ORT_OK;
+    };
+    auto collect = [&](int b, bool *finished) -> int
+    {
+        CUDA_TRY(cudaEventSynchronize(s->wf_done[b]));
+        for(int it = 0; it < WF_BATCH; ++it)
+        {
+            float e = 0.f, so = 0.f, sh = 0.f;
+            cudaEventElapsedTime(&e, s->wf_ev[b][it][0], s->wf_ev[b][it][1]);
+            cudaEventElapsedTime(&so, s->wf_ev[b][it][1], s->wf_ev[b][it][2]);
+            cudaEventElapsedTime(&sh, s->wf_ev[b][it][2], s->wf_ev[b][it][3]);
+            s->extend_ms += e; s->sort_ms += so; s->shade_ms += sh;
+        }
+        *finished = s->h_active[b * WF_BATCH + WF_BATCH - 1] == 0;
+        return ORT_OK;
+    };
+    int cur = 0;
+    bool finished = false;
+    rc = enqueue(cur);
+    if(rc != ORT_OK) return rc;
+    while(!finished)
+    {
+        if(pipelined)
+        {
+            rc = enqueue(cur ^ 1);
+            if(rc != ORT_OK) return rc;
+            rc = collect(cur, &finished);
+            if(rc != ORT_OK) return rc;
+            cur ^= 1;
+            if(finished) { bool dummy; rc = collect(cur, &dummy); if(rc != ORT_OK) return rc; }
+        }
+        else
+        {
+            rc = collect(cur, &finished);
+            if(rc != ORT_OK) return rc;
+            if(!finished) { rc = enqueue(cur); if(rc != ORT_OK) return rc; }
+        }
     }
     return ORT_OK;
 }
@@ -295,6 +346,7 @@ int read_stats(OrtScene *s, cudaStream_t stream, OrtRenderStats *stats, float ms
     stats->samples = h[STAT_SAMPLES]; stats->rays = h[STAT_RAYS];
     stats->node_visits = h[STAT_NODE_VISITS]; stats->box_tests = h[STAT_BOX_TESTS]; stats->shape_tests = h[STAT_SHAPE_TESTS];
     stats->device_ms = ms; stats->kernel_launches = launches;
+    stats->extend_ms = s->extend_ms; stats->shade_ms = s->shade_ms; stats->sort_ms = s->sort_ms;
     return ORT_OK;
 }
 
@@ -400,8 +452,7 @@ int ort_scene_destroy(OrtScene *s)
     if(s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_cyl); cudaFree(s->d_materials);
     cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb);
-    cudaFree(s->wf.ray_o); cudaFree(s->wf.ray_d); cudaFree(s->wf.hit); cudaFree(s->wf.s_wo);
-    cudaFree(s->wf.s_w); cudaFree(s->wf.s_c); cudaFree(s->wf.s_chunk); cudaFree(s->d_active);
+    cudaFree(s->wf.rec); cudaFree(s->d_active);
     cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->d_sort);
     if(s->h_active) cudaFreeHost(s->h_active);
     if(s->ev0) cudaEventDestroy(s->ev0);

@@ -18,14 +18,17 @@
 // stall) with 8 of 32 lanes active on average.  EXTEND alone is a 1600-instruction loop
 // that stays cache resident and runs at 8-10 Grays/s on the same rays.
 //
-// Slot state, structure-of-arrays, 16-byte records (one 128-bit access each):
-//   ray_o   origin.xyz | state word (low 2 bits: DEAD/ACTIVE/FRESH)
-//   ray_d   direction.xyz | 1 if the ray is a primary
-//   hit     t | primitive index                                   (8 bytes)
-//   s_wo    wo.xyz | xorshift state of the stream
-//   s_w     throughput weight.xyz | pixel index
-//   s_c     radiance sum of the stream so far .xyz | samples left (bit 31: ray is a primary)
-//   s_chunk chunk index of the stream                              (4 bytes)
+// Slot state: one 96-byte record per slot = 6 x 16 B = exactly three 32-byte sectors, so the
+// SHADE stage -- which visits slots in material order, i.e. at random addresses -- moves only
+// bytes it uses (a structure-of-arrays layout fetched a 32-byte sector for every 16 bytes and
+// made SHADE HBM-bound: its time fell 23 % just by shrinking the pool into L2).
+//   q0  origin.xyz | state (DEAD / ACTIVE / FRESH)          } EXTEND reads q0,q1: one sector
+//   q1  direction.xyz | 1 if the ray is a primary            }
+//   q2  wo.xyz | xorshift state of the stream
+//   q3  throughput weight.xyz | pixel index
+//   q4  radiance sum of the stream so far .xyz | samples left (bit 31: ray is a primary)
+//   q5  hit t | hit primitive | chunk index of the stream | -      EXTEND writes .xy
+// plus key[] (shading key per slot) and perm[] (slots in key order), 4 B each, coalesced.
 #pragma once
 
 #include "kernels.cuh"
@@ -34,12 +37,11 @@ namespace ort {
 
 enum { WF_DEAD = 0u, WF_ACTIVE = 1u, WF_FRESH = 2u };
 
+#define WF_REC_QUADS 6u
+
 struct WfBuffers
 {
-    float4 *ray_o, *ray_d;
-    uint2 *hit;
-    float4 *s_wo, *s_w, *s_c;
-    uint32_t *s_chunk;
+    float4 *rec;         // WF_REC_QUADS quads per slot
     uint32_t *key;       // shading key written by EXTEND: primary << 8 | min(material, 255); 511 = dead
     uint32_t *perm;      // slots grouped by key (counting sort)
     uint32_t capacity;
@@ -48,7 +50,7 @@ struct WfBuffers
 __global__ void k_wf_reset(WfBuffers wf)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < wf.capacity) wf.ray_o[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_FRESH));
+    if(i < wf.capacity) wf.rec[WF_REC_QUADS * i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_FRESH));
 }
 
 // shared-memory traversal stack: entry k of thread t lives at column t of row k, so the 32
@@ -111,10 +113,10 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned lon
             uint32_t my = next + __popc(idle_mask & ((1u << lane) - 1u));
             if(!has_ray && my < end)
             {
-                float4 ro = wf.ray_o[my];
+                float4 ro = wf.rec[WF_REC_QUADS * my];
                 if(__float_as_uint(ro.w) == WF_ACTIVE)
                 {
-                    float4 rd = wf.ray_d[my];
+                    float4 rd = wf.rec[WF_REC_QUADS * my + 1u];
                     trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
                     is_primary = __float_as_uint(rd.w);
                     slot = my;
@@ -138,7 +140,7 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned lon
             if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; shapes += cnt.shape_tests; }
             if(done)
             {
-                wf.hit[slot] = make_uint2(__float_as_uint(t.best_t), t.best_prim);
+                *reinterpret_cast<uint2 *>(wf.rec + WF_REC_QUADS * slot + 5u) = make_uint2(__float_as_uint(t.best_t), t.best_prim);
                 uint32_t mat = 0u;
                 if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
                 uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
@@ -259,7 +261,8 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
     }
     if(in_range)
     {
-        float4 ro = wf.ray_o[i];
+        float4 *rec = wf.rec + (size_t)WF_REC_QUADS * i;
+        float4 ro = rec[0];
         uint32_t state = __float_as_uint(ro.w);
         if(state != WF_DEAD)
         {
@@ -269,9 +272,9 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
             bool have_ray = false;
             if(state == WF_ACTIVE)
             {
-                float4 rd = wf.ray_d[i], swo = wf.s_wo[i], sw = wf.s_w[i], scol = wf.s_c[i];
-                uint2 h = wf.hit[i];
-                chunk = wf.s_chunk[i];
+                float4 rd = rec[1], swo = rec[2], sw = rec[3], scol = rec[4], hq = rec[5];
+                uint2 h = make_uint2(__float_as_uint(hq.x), __float_as_uint(hq.y));
+                chunk = __float_as_uint(hq.z);
                 p.origin = mk3(ro.x, ro.y, ro.z); p.dir = mk3(rd.x, rd.y, rd.z);
                 p.wo = mk3(swo.x, swo.y, swo.z); p.series = __float_as_uint(swo.w);
                 p.weight = mk3(sw.x, sw.y, sw.z); pixel_index = __float_as_uint(sw.w);
@@ -341,7 +344,7 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
                 }
                 if(dead)
                 {
-                    wf.ray_o[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_DEAD));
+                    rec[0] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_DEAD));
                 }
                 else
                 {
@@ -356,13 +359,13 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
             }
             if(have_ray)
             {
-                wf.ray_o[i] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
-                wf.ray_d[i] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(primary_next ? 1u : 0u));
-                wf.s_wo[i] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
-                wf.s_w[i] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
-                wf.s_c[i] = make_float4(color.x, color.y, color.z,
-                                        __uint_as_float(samples_left | (primary_next ? 0x80000000u : 0u)));
-                wf.s_chunk[i] = chunk;
+                rec[0] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
+                rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(primary_next ? 1u : 0u));
+                rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
+                rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
+                rec[4] = make_float4(color.x, color.y, color.z,
+                                     __uint_as_float(samples_left | (primary_next ? 0x80000000u : 0u)));
+                rec[5] = make_float4(0.f, 0.f, __uint_as_float(chunk), 0.f);
                 still_active = 1;
             }
         }

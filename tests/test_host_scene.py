@@ -31,7 +31,7 @@ def test_abi_exports_every_declared_symbol(ort):
 def test_struct_layouts_match_header(ort):
     assert C.sizeof(ort.Camera) == 48
     assert C.sizeof(ort.RenderParams) == 80
-    assert C.sizeof(ort.RenderStats) == 48
+    assert C.sizeof(ort.RenderStats) == 64
 
 
 def test_number_tokens_golden(ort):

@@ -23,5 +23,6 @@ sc = ort.Scene(hs.world, hs.root, 0, library=ort.lib(os.path.abspath(a.lib)) if 
 P = ort.default_params(a.width, a.height, a.spp, chunk_spp=a.chunk, kernel=a.kernel)
 for _ in range(a.reps):
     img, st = sc.render(hs.camera, P)
-print("ms %.3f  Msamples/s %.1f  Mrays/s %.1f  rays/sample %.3f" % (
-    st["device_ms"], st["samples"] / st["device_ms"] / 1e3, st["rays"] / st["device_ms"] / 1e3, st["rays"] / st["samples"]))
+print("ms %.3f  Msamples/s %.1f  Mrays/s %.1f  rays/sample %.3f | extend %.2f sort %.2f shade %.2f ms, %d launches" % (
+    st["device_ms"], st["samples"] / st["device_ms"] / 1e3, st["rays"] / st["device_ms"] / 1e3, st["rays"] / st["samples"],
+    st["extend_ms"], st["sort_ms"], st["shade_ms"], st["kernel_launches"]))
