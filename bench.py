@@ -233,13 +233,15 @@ def main_gpu(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
     ms = float(ms.item())
-    gpu_launches = launches[0]
     samples_per_step = WIDTH * HEIGHT * spp_total
     value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
 
     # kernel-only time and ray counts of one step (this rank), for the roofline
     st = scene.render_accumulate_device(hs.camera, P, accum.data_ptr(), stream=stream, want_stats=True)
     kernel_ms, rays, samples = st["device_ms"], st["rays"], st["samples"]
+    # every kernel this library launches in one step (wavefront: extend/scan/scatter/shade per
+    # iteration) + the resolve on rank 0
+    gpu_launches = (st["kernel_launches"] + (1 if rank == 0 else 0)) * args.steps
 
     # ---- e2e: through the C ABI with host buffers ----
     e2e_ms = None
@@ -294,6 +296,11 @@ def main_gpu(args):
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     fp32_peak = ort.measure_fp32_peak(local)
     rays_per_s = rays / (kernel_ms * 1e-3)
+    # dominant kernel: EXTEND (k_wf_extend); its launches are timed live with CUDA events on the
+    # launching stream inside the library (OrtRenderStats.extend_ms = sum over the step's launches)
+    extend_ms = st["extend_ms"] if st["extend_ms"] > 0 else kernel_ms
+    n_extend = max(1, (st["kernel_launches"] - 2) // 4)
+    extend_rays_per_s = rays / (extend_ms * 1e-3)
     roofline = roofline_fp32 = None
     if per_ray and "error" not in per_ray:
         bytes_per_ray = 48.0 * per_ray["shape_tests"] + info["bvh_node_bytes"] * per_ray["node_visits"]
@@ -305,13 +312,14 @@ def main_gpu(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        a = bytes_per_ray * rays_per_s / 1e9
+        a = bytes_per_ray * extend_rays_per_s / 1e9
         roofline = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": traffic,
-                    "peak_source": peak_src, "kernel": "k_render_mega", "launch_ms": kernel_ms,
-                    "algorithmic_bytes_per_ray": bytes_per_ray,
+                    "peak_source": peak_src, "kernel": "k_wf_extend", "launch_ms": extend_ms / n_extend,
+                    "launches_per_step": n_extend, "share_of_step": extend_ms / kernel_ms,
+                    "algorithmic_bytes_per_ray": bytes_per_ray, "algorithmic_bytes_per_launch": bytes_per_ray * rays / n_extend,
                     "note": "scene (%.1f MB) is L2/L1-resident by design; the binding limit is the FP32/issue pipe, see roofline_fp32"
                             % (info["device_bytes"] / 1e6)}
-        f = flops_per_ray * rays_per_s / 1e12
+        f = flops_per_ray * extend_rays_per_s / 1e12
         roofline_fp32 = {"bound": "fp32", "achieved": f, "peak": fp32_peak, "unit": "TFLOP/s", "frac": f / fp32_peak,
                          "peak_source": "measured in this run: FMUL+FADD chain kernel (no FMA), ort_measure_fp32_peak",
                          "algorithmic_flops_per_ray": flops_per_ray}
@@ -329,7 +337,8 @@ def main_gpu(args):
                      "parallelism": "sample-chunk split x%d, ncclReduce(int64 sum)" % world if world > 1 else "1 GPU",
                      "cache": "L2 flushed between steps (256 MiB memset); the 10 MB scene is re-fetched from HBM each step"},
           "mrays_per_s": rays_per_s * world / 1e6, "rays_per_sample": rays / max(1, samples),
-          "kernel_ms_per_step": kernel_ms, "per_ray_work": per_ray,
+          "kernel_ms_per_step": kernel_ms, "stage_ms_per_step": {"extend": st["extend_ms"], "sort": st["sort_ms"], "shade": st["shade_ms"]},
+          "per_ray_work": per_ray,
           "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                   "api": "ort_render (host v3 buffer)" if world == 1 else "ort_render_accumulate_device + ncclReduce + D2H"},
           "gpu_launches": gpu_launches, "clocks": clocks,

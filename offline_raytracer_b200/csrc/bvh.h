@@ -90,8 +90,10 @@ struct SceneView
     // are traversed WITHOUT clipping to the best hit so far: a ray tangent to a
     // sphere is reported by the reference at t = -b/(2a), half way to the sphere
     // (code/ray.cpp:174-183), so a nearer hit must not cull the sphere's box.
-    // The main tree (everything else) starts at main_root and is clipped.
+    // The clipped trees follow: boxes + cylinders in [main_root, tri_root) (absent if equal),
+    // triangles from tri_root.
     uint32_t main_root;
+    uint32_t tri_root;
 };
 
 struct TraceCounters { uint32_t node_visits, box_tests, shape_tests; };
@@ -178,16 +180,22 @@ ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
     t.o = o; t.d = d;
     t.best_t = FLT_MAX; t.best_prim = 0xFFFFFFFFu; t.best_rank = 0xFFFFFFFFu;
     t.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    // node group: a root as the single hit child of a virtual parent (imask 0 => relative index 0)
+    // node group: a root as the single hit child of a virtual parent (imask 0 => relative index 0).
+    // Order: analytic shapes (their hit clips what follows), triangles, spheres (unclipped).
     t.ng_x = s.main_root; t.ng_y = 0x80000000u;
     t.sp = 0;
-    if(s.main_root != 0u) { st.put(0, 0u, 0x80000000u); t.sp = 1; }   // sphere tree, visited last
+    if(s.main_root != 0u) { st.put(t.sp, 0u, 0x80000000u); ++t.sp; }
+    if(s.tri_root != s.main_root) { st.put(t.sp, s.tri_root, 0x80000000u); ++t.sp; }
 }
 
-// One step: visit one wide node (if a node group is pending), test the primitives it
-// yielded, pop.  Returns true when the traversal is complete.
+// Visits the nearest pending child of the current node group (which must have node bits set):
+// tests its 8 children against the ray clipped to [0, clip_t], leaves the hit inner children in
+// the node group and returns the hit leaf primitives as a group (base index, bit mask) plus the
+// index of the node visited (its tree decides the kind of the primitives and whether clip_t
+// applies: nodes below main_root -- the sphere tree -- are never clipped).
 template <bool COUNT, class Stack>
-ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt)
+ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, TraceCounters *cnt,
+                       uint32_t *tg_x_out, uint32_t *tg_y_out, uint32_t *node_index_out)
 {
     // reciprocal direction of the (conservative) slab tests: the exact one, except that zero and
     // denormal-small components are clamped so that 0 * inf never appears
@@ -197,81 +205,93 @@ ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt
     const float idz = fabsf(t.d.z) > tiny ? t.inv.z : (f2u(t.d.z) >> 31 ? -huge : huge);
     const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
     const uint32_t octinv = 7u - ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
-    uint32_t tg_x = 0u, tg_y = 0u;        // primitive group
+
+    uint32_t bit = msb32(t.ng_y);
+    uint32_t hits_imask = t.ng_y;
+    t.ng_y &= ~(1u << bit);
     if(t.ng_y & 0xFF000000u)
     {
-        uint32_t bit = msb32(t.ng_y);
-        uint32_t hits_imask = t.ng_y;
-        t.ng_y &= ~(1u << bit);
-        if(t.ng_y & 0xFF000000u)
-        {
-            if(t.sp < ORT_STACK_SIZE) { st.put(t.sp, t.ng_x, t.ng_y); ++t.sp; }
-        }
-        uint32_t slot = (bit - 24u) ^ octinv;
-        uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-        const uint32_t node_index = t.ng_x + rel;
-        const float t_clip = (node_index >= s.main_root) ? t.best_t : FLT_MAX;
-        const q4 *np = s.nodes + 5u * node_index;
-        q4 n0 = ldq(np), n1 = ldq(np + 1), n2 = ldq(np + 2), n3 = ldq(np + 3), n4 = ldq(np + 4);
-        if(COUNT) cnt->node_visits++;
-
-        uint32_t e_imask = f2u(n0.w);
-        float ax = u2f((e_imask & 0xFFu) << 23) * idx;
-        float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * idy;
-        float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * idz;
-        float bx = (n0.x - t.o.x) * idx;
-        float by = (n0.y - t.o.y) * idy;
-        float bz = (n0.z - t.o.z) * idz;
-
-        t.ng_x = f2u(n1.x);
-        tg_x = f2u(n1.y);
-        uint32_t hitmask = 0u;
-        const uint32_t octinv4 = octinv * 0x01010101u;
-#pragma unroll
-        for(int half = 0; half < 2; ++half)
-        {
-            uint32_t meta4 = half ? f2u(n1.w) : f2u(n1.z);
-            uint32_t lox = half ? f2u(n2.y) : f2u(n2.x);
-            uint32_t loy = half ? f2u(n2.w) : f2u(n2.z);
-            uint32_t loz = half ? f2u(n3.y) : f2u(n3.x);
-            uint32_t hix = half ? f2u(n3.w) : f2u(n3.z);
-            uint32_t hiy = half ? f2u(n4.y) : f2u(n4.x);
-            uint32_t hiz = half ? f2u(n4.w) : f2u(n4.z);
-            uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
-            uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
-            uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
-            // per byte: inner children (low 5 bits >= 24, i.e. bits 3 and 4 set) get their slot
-            // XORed with octinv so that the highest hit bit is the nearest child
-            uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-            uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
-            uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-            uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#pragma unroll
-            for(uint32_t k = 0; k < 4; ++k)
-            {
-                float t0x = fmaf(byte_f(nearx, k), ax, bx);
-                float t0y = fmaf(byte_f(neary, k), ay, by);
-                float t0z = fmaf(byte_f(nearz, k), az, bz);
-                float t1x = fmaf(byte_f(farx, k), ax, bx);
-                float t1y = fmaf(byte_f(fary, k), ay, by);
-                float t1z = fmaf(byte_f(farz, k), az, bz);
-                float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-                float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
-                if(COUNT) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
-                uint32_t child_bits = (child_bits4 >> (8u * k)) & 0xFFu;
-                uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
-                hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
-            }
-        }
-        t.ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);
-        tg_y = hitmask & 0x00FFFFFFu;
+        if(t.sp < ORT_STACK_SIZE) { st.put(t.sp, t.ng_x, t.ng_y); ++t.sp; }
     }
-    else
+    uint32_t slot = (bit - 24u) ^ octinv;
+    uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+    const uint32_t node_index = t.ng_x + rel;
+    const float t_clip = (node_index >= s.main_root) ? clip_t : FLT_MAX;
+    const q4 *np = s.nodes + 5u * node_index;
+    q4 n0 = ldq(np), n1 = ldq(np + 1), n2 = ldq(np + 2), n3 = ldq(np + 3), n4 = ldq(np + 4);
+    if(COUNT) cnt->node_visits++;
+
+    uint32_t e_imask = f2u(n0.w);
+    float ax = u2f((e_imask & 0xFFu) << 23) * idx;
+    float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * idy;
+    float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * idz;
+    float bx = (n0.x - t.o.x) * idx;
+    float by = (n0.y - t.o.y) * idy;
+    float bz = (n0.z - t.o.z) * idz;
+
+    t.ng_x = f2u(n1.x);
+    uint32_t hitmask = 0u;
+    const uint32_t octinv4 = octinv * 0x01010101u;
+#pragma unroll
+    for(int half = 0; half < 2; ++half)
     {
-        tg_x = t.ng_x; tg_y = t.ng_y;
-        t.ng_x = 0u; t.ng_y = 0u;
+        uint32_t meta4 = half ? f2u(n1.w) : f2u(n1.z);
+        uint32_t lox = half ? f2u(n2.y) : f2u(n2.x);
+        uint32_t loy = half ? f2u(n2.w) : f2u(n2.z);
+        uint32_t loz = half ? f2u(n3.y) : f2u(n3.x);
+        uint32_t hix = half ? f2u(n3.w) : f2u(n3.z);
+        uint32_t hiy = half ? f2u(n4.y) : f2u(n4.x);
+        uint32_t hiz = half ? f2u(n4.w) : f2u(n4.z);
+        uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+        uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+        uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+        // per byte: inner children (low 5 bits >= 24, i.e. bits 3 and 4 set) get their slot
+        // XORed with octinv so that the highest hit bit is the nearest child
+        uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
+        uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+        uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+        for(uint32_t k = 0; k < 4; ++k)
+        {
+            float t0x = fmaf(byte_f(nearx, k), ax, bx);
+            float t0y = fmaf(byte_f(neary, k), ay, by);
+            float t0z = fmaf(byte_f(nearz, k), az, bz);
+            float t1x = fmaf(byte_f(farx, k), ax, bx);
+            float t1y = fmaf(byte_f(fary, k), ay, by);
+            float t1z = fmaf(byte_f(farz, k), az, bz);
+            float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+            float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
+            if(COUNT) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
+            uint32_t child_bits = (child_bits4 >> (8u * k)) & 0xFFu;
+            uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
+            hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
+        }
     }
+    t.ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);
+    *tg_x_out = f2u(n1.y);
+    *tg_y_out = hitmask & 0x00FFFFFFu;
+    *node_index_out = node_index;
+}
 
+// Pops the next pending node group when the current one is exhausted; false = traversal done.
+template <class Stack>
+ORT_HD bool trav_next(Trav &t, Stack &st)
+{
+    if(t.ng_y & 0xFF000000u) return true;
+    if(t.sp == 0) return false;
+    --t.sp;
+    st.get(t.sp, t.ng_x, t.ng_y);
+    return true;
+}
+
+// One step: visit one wide node, test the primitives it yielded, pop.  Returns true when the
+// traversal is complete.
+template <bool COUNT, class Stack>
+ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt)
+{
+    uint32_t tg_x = 0u, tg_y = 0u, node_index = 0u;
+    if(t.ng_y & 0xFF000000u) trav_visit<COUNT>(s, t, st, t.best_t, cnt, &tg_x, &tg_y, &node_index);
     while(tg_y)
     {
         uint32_t bit = lsb32(tg_y);
@@ -286,14 +306,7 @@ ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt
             t.best_t = h.t; t.best_prim = prim; t.best_rank = rank;
         }
     }
-
-    if(!(t.ng_y & 0xFF000000u))
-    {
-        if(t.sp == 0) return true;
-        --t.sp;
-        st.get(t.sp, t.ng_x, t.ng_y);
-    }
-    return false;
+    return !trav_next(t, st);
 }
 
 // Closest hit.  COUNT adds work counters (the counters build of the same code,

@@ -36,7 +36,8 @@ struct OrtScene
 {
     int device;
     OrtSceneInfo info;
-    uint32_t main_root;
+    uint32_t main_root, tri_root;
+    uint32_t *d_rank_to_prim;
     // device arrays (layout: bvh.h, scene_flatten.h)
     q4 *d_nodes, *d_prims, *d_cyl, *d_materials;
     uint8_t *d_light_is_sphere;
@@ -49,7 +50,7 @@ struct OrtScene
     cudaEvent_t ev0, ev1;
     int sm_count;
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
-    int wf_extend_blocks;
+    int wf_extend_blocks, wf_extend_q_blocks;
     uint32_t stack_rows;                // wide-tree depth + 1: rows of the shared-memory traversal stack
     int wf_events_ready;
     cudaEvent_t wf_done[2], wf_ev[2][8][4];
@@ -64,7 +65,7 @@ struct OrtScene
     {
         SceneView v;
         v.nodes = d_nodes; v.prims = d_prims; v.cyl = d_cyl;
-        v.node_count = node_count; v.prim_count = prim_count; v.main_root = main_root;
+        v.node_count = node_count; v.prim_count = prim_count; v.main_root = main_root; v.tri_root = tri_root;
         return v;
     }
 };
@@ -167,7 +168,7 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
     s->wf.capacity = capacity;
     if(!s->d_active)
     {
-        CUDA_TRY(cudaMalloc((void **)&s->d_sort, (2 * WF_KEY_BINS + 1) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc((void **)&s->d_sort, (2 * WF_KEY_BINS + 2) * sizeof(uint32_t)));
         CUDA_TRY(cudaMalloc((void **)&s->d_active, 2 * WF_BATCH * sizeof(unsigned int)));
         CUDA_TRY(cudaMallocHost((void **)&s->h_active, 2 * WF_BATCH * sizeof(unsigned int)));
     }
@@ -202,6 +203,18 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     const uint32_t warps = egrid * 4u;
     const uint32_t slots_per_warp = ((capacity + warps - 1u) / warps + 31u) & ~31u;
     uint32_t *hist = s->d_sort, *cursor = s->d_sort + WF_KEY_BINS, *live = s->d_sort + 2 * WF_KEY_BINS;
+    uint32_t *chunk_counter = s->d_sort + 2 * WF_KEY_BINS + 1;
+    // 0 = k_wf_extend (default); 1 = k_wf_extend_q, the test-redistributing variant -- measured
+    // slower on B200 (238 vs 202 ms of EXTEND per 1080p x 128 spp): rays wait for their queued tests
+    const int extend_q = getenv("ORT_WF_EXTEND") ? atoi(getenv("ORT_WF_EXTEND")) : 0;
+    if(s->wf_extend_q_blocks == 0)
+    {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend_q<false>, 128, s->stack_rows * 128 * sizeof(uint2)));
+        s->wf_extend_q_blocks = (nb > 0 ? nb : 1) * s->sm_count;
+    }
+    unsigned qgrid = (unsigned)s->wf_extend_q_blocks;
+    if((unsigned long long)qgrid * 128ull > capacity) qgrid = (capacity + 127u) / 128u;
     if(!s->wf_events_ready)
     {
         for(int b = 0; b < 2; ++b)
@@ -227,12 +240,24 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         for(int it = 0; it < WF_BATCH; ++it)
         {
             CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), stream));
+            CUDA_TRY(cudaMemsetAsync(chunk_counter, 0, sizeof(uint32_t), stream));
             CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][0], stream));
+            if(extend_q)
+            {
 #ifdef ORT_COUNTERS
-            k_wf_extend<true><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+                k_wf_extend_q<true><<<qgrid, 128, stack_bytes, stream>>>(a.scene, wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
 #else
-            k_wf_extend<false><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+                k_wf_extend_q<false><<<qgrid, 128, stack_bytes, stream>>>(a.scene, wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
 #endif
+            }
+            else
+            {
+#ifdef ORT_COUNTERS
+                k_wf_extend<true><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+#else
+                k_wf_extend<false><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+#endif
+            }
             CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][1], stream));
             if(sorted)
             {
@@ -412,6 +437,7 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     BuildOptions opt;
     if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
+    if(const char *e = getenv("ORT_BVH_MERGE_SHAPES")) opt.merge_shapes = atoi(e) != 0;
     int rc = flatten_scene(world, top_most_node, opt, &flat, &err);
     if(rc != ORT_OK) return fail(rc, err);
 
@@ -421,7 +447,8 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     s->device = device;
     s->info = flat.info;
     s->main_root = flat.main_root;
-    s->stack_rows = flat.wide_depth + 1u;
+    s->tri_root = flat.tri_root;
+    s->stack_rows = flat.wide_depth + 2u;
     s->node_count = (uint32_t)flat.nodes.size();
     s->prim_count = (uint32_t)flat.prims.size();
     s->light_count = (uint32_t)flat.light_is_sphere.size();
@@ -431,6 +458,7 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     if(rc == ORT_OK) rc = upload(&s->d_cyl, flat.cylinders.data(), flat.cylinders.size() * sizeof(CylinderAux), &total);
     if(rc == ORT_OK) rc = upload(&s->d_materials, flat.materials.data(), flat.materials.size() * sizeof(DevMaterial), &total);
     if(rc == ORT_OK) rc = upload(&s->d_light_is_sphere, flat.light_is_sphere.data(), flat.light_is_sphere.size(), &total);
+    if(rc == ORT_OK) rc = upload(&s->d_rank_to_prim, flat.rank_to_prim.data(), flat.rank_to_prim.size() * sizeof(uint32_t), &total);
     if(rc == ORT_OK) rc = upload(&s->d_stats, (const void *)0, 0, &total);
     if(rc != ORT_OK) { ort_scene_destroy(s); return rc; }
     cudaFree(s->d_stats); s->d_stats = 0;
@@ -450,6 +478,7 @@ int ort_scene_destroy(OrtScene *s)
     if(!s) return ORT_OK;
     cudaSetDevice(s->device);
     if(s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_rank_to_prim);
     cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_cyl); cudaFree(s->d_materials);
     cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb);
     cudaFree(s->wf.rec); cudaFree(s->d_active);

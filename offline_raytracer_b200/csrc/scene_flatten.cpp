@@ -557,7 +557,7 @@ int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatSc
             scene_abs = std::max(scene_abs, fabs((double)prims[i].lo[k]));
             scene_abs = std::max(scene_abs, fabs((double)prims[i].hi[k]));
         }
-    std::vector<HostPrim> spheres, others;
+    std::vector<HostPrim> spheres, shapes, tris;
     for(size_t i = 0; i < prims.size(); ++i)
     {
         HostPrim &p = prims[i];
@@ -583,27 +583,45 @@ int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatSc
             p.lo[k] = nextafterf((float)((double)p.lo[k] - pad), -INFINITY);
             p.hi[k] = nextafterf((float)((double)p.hi[k] + pad), INFINITY);
         }
-        if(p.kind == PRIM_SPHERE) spheres.push_back(p); else others.push_back(p);
+        if(p.kind == PRIM_SPHERE) spheres.push_back(p);
+        else if(p.kind == PRIM_TRIANGLE || opt.merge_shapes) tris.push_back(p);
+        else shapes.push_back(p);
     }
     std::vector<HostPrim>().swap(prims);
-    out->prims.reserve(spheres.size() + others.size());
+    out->prims.reserve(spheres.size() + shapes.size() + tris.size());
 
-    uint32_t d0 = 0, d1 = 0;
+    // Three trees share the node array, in this order:
+    //   [0, main_root)         spheres            -- traversed UNCLIPPED (see above)
+    //   [main_root, tri_root)  boxes + cylinders  -- the few analytic shapes; typically the room
+    //   [tri_root, ...)        triangles
+    // so the kind of a leaf's records follows from the node index, primitive tests of one kind
+    // run together, and the shapes (tested first) give an early bound that clips the triangles.
+    uint32_t d0 = 0, d1 = 0, d2 = 0;
     if(!spheres.empty())
     {
         int rc = emit_tree(spheres, opt, out, &d0, err);
         if(rc != ORT_OK) return rc;
     }
     out->main_root = (uint32_t)out->nodes.size();
-    int rc = emit_tree(others, opt, out, &d1, err);
+    if(!shapes.empty())
+    {
+        int rc = emit_tree(shapes, opt, out, &d1, err);
+        if(rc != ORT_OK) return rc;
+    }
+    out->tri_root = (uint32_t)out->nodes.size();
+    int rc = emit_tree(tris, opt, out, &d2, err);
     if(rc != ORT_OK) return rc;
-    out->wide_depth = std::max(d0, d1);
-    // every level pushes at most one pending node group; +1 for the sphere tree's root entry
-    if(out->wide_depth + 1 > ORT_STACK_SIZE)
+    out->wide_depth = std::max(d0, std::max(d1, d2));
+    // every level pushes at most one pending node group; +2 for the other trees' root entries
+    if(out->wide_depth + 2 > ORT_STACK_SIZE)
     {
         *err = "wide BVH deeper than the traversal stack";
         return ORT_ERR_LIMIT;
     }
+    // rank -> record index, for kernels that carry (t, rank) only
+    out->rank_to_prim.assign(out->info.record_count, 0xFFFFFFFFu);
+    for(size_t i = 0; i < out->prims.size(); ++i)
+        if(out->prims[i].rank < out->rank_to_prim.size()) out->rank_to_prim[out->prims[i].rank] = (uint32_t)i;
     out->info.bvh_node_count = (uint32_t)out->nodes.size();
     out->info.bvh_node_bytes = (uint32_t)sizeof(WideNode);
     return ORT_OK;

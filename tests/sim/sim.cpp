@@ -37,6 +37,7 @@ void *sim_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *root, floa
     s->view.node_count = (uint32_t)s->flat.nodes.size();
     s->view.prim_count = (uint32_t)s->flat.prims.size();
     s->view.main_root = s->flat.main_root;
+    s->view.tri_root = s->flat.tri_root;
     return s;
 }
 void sim_scene_destroy(void *h) { delete (SimScene *)h; }
