@@ -178,3 +178,33 @@ def test_bad_arguments(ort, gpu_scene, testscene_host):
     P.kernel = 77
     with pytest.raises(ort.OrtError):
         gpu_scene.render(testscene_host.camera, P)
+
+
+def test_wavefront_and_megakernel_are_bit_identical(ort, gpu_scene, testscene_host):
+    """the two kernel families schedule the same per-stream arithmetic differently; every pixel
+    must come out bit-identical (float single-chunk mode and fixed-point chunked mode)"""
+    for chunk in (0, 4):
+        imgs = []
+        for kernel in (ort.ORT_KERNEL_MEGAKERNEL, ort.ORT_KERNEL_WAVEFRONT):
+            P = ort.default_params(W, H, 8, chunk_spp=chunk, kernel=kernel)
+            img, st = gpu_scene.render(testscene_host.camera, P)
+            assert st["samples"] == W * H * 8
+            imgs.append(img)
+        assert np.array_equal(bits(imgs[0]), bits(imgs[1])), chunk
+
+
+def test_wavefront_small_pool_and_unsorted_give_the_same_image(ort, testscene_host, monkeypatch):
+    """pool size and the material sort only change scheduling, never a pixel"""
+    P = ort.default_params(W, H, 6, chunk_spp=2, kernel=ort.ORT_KERNEL_WAVEFRONT)
+    sc = ort.Scene(testscene_host.world, testscene_host.root, 0)
+    base, _ = sc.render(testscene_host.camera, P)
+    monkeypatch.setenv("ORT_WF_SLOTS", "20000")
+    small, st = sc.render(testscene_host.camera, P)
+    assert np.array_equal(bits(base), bits(small)) and st["kernel_launches"] > 100
+    monkeypatch.setenv("ORT_WF_NOSORT", "1")
+    unsorted, _ = sc.render(testscene_host.camera, P)
+    assert np.array_equal(bits(base), bits(unsorted))
+    monkeypatch.delenv("ORT_WF_NOSORT"); monkeypatch.setenv("ORT_WF_EXTEND", "1")
+    queued, _ = sc.render(testscene_host.camera, P)
+    assert np.array_equal(bits(base), bits(queued))
+    sc.close()
