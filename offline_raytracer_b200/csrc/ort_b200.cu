@@ -200,8 +200,6 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     }
     unsigned egrid = (unsigned)s->wf_extend_blocks;
     if(egrid > grid) egrid = grid;
-    const uint32_t warps = egrid * 4u;
-    const uint32_t slots_per_warp = ((capacity + warps - 1u) / warps + 31u) & ~31u;
     uint32_t *hist = s->d_sort, *cursor = s->d_sort + WF_KEY_BINS, *live = s->d_sort + 2 * WF_KEY_BINS;
     uint32_t *chunk_counter = s->d_sort + 2 * WF_KEY_BINS + 1;
     // 0 = k_wf_extend (default); 1 = k_wf_extend_q, the test-redistributing variant -- measured
@@ -253,9 +251,9 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
             else
             {
 #ifdef ORT_COUNTERS
-                k_wf_extend<true><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+                k_wf_extend<true><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, chunk_counter, a.stats, hist);
 #else
-                k_wf_extend<false><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, slots_per_warp, a.stats, hist);
+                k_wf_extend<false><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, chunk_counter, a.stats, hist);
 #endif
             }
             CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][1], stream));

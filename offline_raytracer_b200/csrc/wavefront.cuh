@@ -73,30 +73,37 @@ struct SharedStack
 // per trip.  Also emits the slot's shading key (primary flag, material of the hit) and counts it,
 // for the counting sort that groups SHADE by material.
 // resident 4-warp blocks per SM the register allocation must allow (measured on B200, 1080p:
-// extend 8 / shade 6 = 116 ms; 6/6 = 119 ms; unconstrained (96 / 89 registers) = 127 ms)
+// extend 8 / shade 6 = 116 ms; 6/6 = 119 ms; unconstrained (96 / 89 registers) = 127 ms;
+// after the 96-byte slot records: shade 6 / 7 / 8 / 10 blocks = 139.8 / 135.1 / 131.3 / 138.1 ms per 1080p x 128 spp)
 #ifndef ORT_EXTEND_MIN_BLOCKS
 #define ORT_EXTEND_MIN_BLOCKS 8
 #endif
 #ifndef ORT_SHADE_MIN_BLOCKS
-#define ORT_SHADE_MIN_BLOCKS 6
+#define ORT_SHADE_MIN_BLOCKS 8
 #endif
 // dynamic shared memory: (wide-tree depth + 1) stack rows of 128 uint2 -- sized per scene, so a
 // shallow tree does not pay for ORT_STACK_SIZE rows of occupancy
+#ifndef ORT_FETCH_MIN
+#define ORT_FETCH_MIN 8      // refill when at least this many lanes are idle (or none has a ray)
+#endif
+#define WF_CHUNK 256u        // slots a warp takes from the global counter at a time
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
-k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned long long *stats, uint32_t *hist)
+k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned long long *stats, uint32_t *hist)
 {
     extern __shared__ uint2 smem_stack[];
     __shared__ uint32_t sh_hist[WF_KEY_BINS];
+    __shared__ uint32_t sh_done;
+    if(threadIdx.x == 0) sh_done = 0u;
     for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh_hist[k] = 0u;
     __syncthreads();
     SharedStack st; st.col = smem_stack + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    unsigned long long range_lo = (unsigned long long)warp * slots_per_warp;
-    uint32_t next = (uint32_t)(range_lo < wf.capacity ? range_lo : wf.capacity);
-    unsigned long long range_hi_l = range_lo + slots_per_warp;
-    const uint32_t end = (uint32_t)(range_hi_l < wf.capacity ? range_hi_l : wf.capacity);
+    // slot ranges are handed out in chunks from a global counter, so that all warps of the grid
+    // finish together (static ranges left SMs half empty at the end of every launch)
+    uint32_t next = 0u, end = 0u;
+    bool exhausted = false;
 
     Trav t;
     t.ng_x = t.ng_y = 0u; t.sp = 0;
@@ -107,9 +114,18 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned lon
     for(;;)
     {
         uint32_t idle_mask = __ballot_sync(0xFFFFFFFFu, !has_ray);
-        if(idle_mask != 0u && next < end)
+        if(!exhausted && (__popc(idle_mask) >= ORT_FETCH_MIN || idle_mask == 0xFFFFFFFFu))
         {
-            // hand consecutive slots of the range to the idle lanes
+            if(next >= end)
+            {
+                uint32_t base = 0u;
+                if(lane == 0) base = atomicAdd(chunk_counter, WF_CHUNK);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                next = base; end = base + WF_CHUNK;
+                if(end > wf.capacity) end = wf.capacity;
+                if(base >= wf.capacity) { exhausted = true; next = end = 0u; }
+            }
+            // hand consecutive slots of the chunk to the idle lanes
             uint32_t my = next + __popc(idle_mask & ((1u << lane) - 1u));
             if(!has_ray && my < end)
             {
@@ -130,13 +146,15 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned lon
         }
         if(__ballot_sync(0xFFFFFFFFu, has_ray) == 0u)
         {
-            if(next >= end) break;
+            if(exhausted) break;
             continue;
         }
-        if(has_ray)
         {
             TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
-            bool done = trav_step<COUNT>(scene, t, st, &cnt);
+            // (tried and rejected, B200, C3: postponing the primitive tests of a step until >= 8 lanes
+            //  have some, after Ylitie et al. 2017 -- EXTEND 349 ms vs 179 ms: the hit bound arrives late
+            //  and far more nodes are visited)
+            bool done = has_ray && trav_step<COUNT>(scene, t, st, &cnt);
             if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; shapes += cnt.shape_tests; }
             if(done)
             {
@@ -162,9 +180,21 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned lon
             atomicAdd(&stats[STAT_SHAPE_TESTS], shapes);
         }
     }
-    // the block's share of the key histogram (first pass of the counting sort)
-    __syncthreads();
-    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) if(sh_hist[k]) atomicAdd(&hist[k], sh_hist[k]);
+    // the block's share of the key histogram (first pass of the counting sort), flushed by
+    // whichever of its warps finishes last -- no barrier for the others to wait at
+    __syncwarp();
+    uint32_t finished = 0u;
+    if(lane == 0) { __threadfence_block(); finished = atomicAdd(&sh_done, 1u); }
+    finished = __shfl_sync(0xFFFFFFFFu, finished, 0);
+    if(finished == 3u)
+    {
+        __threadfence_block();
+        for(uint32_t k = lane; k < WF_KEY_BINS; k += 32u)
+        {
+            uint32_t v = ((volatile uint32_t *)sh_hist)[k];
+            if(v) atomicAdd(&hist[k], v);
+        }
+    }
 }
 
 // EXTEND with primitive-test redistribution.
@@ -181,7 +211,6 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t slots_per_warp, unsigned lon
 // wins".  Culling reads the same word, so it only ever uses a bound that is already proven.
 // Slot ranges are handed out in chunks from a global counter, so warps finish together.
 #define WF_QCAP 128u
-#define WF_CHUNK 256u
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
