@@ -11,7 +11,11 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <deque>
+#include <mutex>
+#include <thread>
 
 namespace ort {
 
@@ -250,6 +254,87 @@ struct Builder
 
     Builder(const std::vector<HostPrim> &p, const BuildOptions &o) : prims(p), opt(o) {}
 
+    struct Job { uint32_t node, first, count; };
+
+    // Binned-SAH split of one node.  Returns false for a leaf; else fills the two child jobs.
+    bool split(const Job &job, std::atomic<uint32_t> &next_node, Job *left, Job *right)
+    {
+        const int NBINS = 16;
+        Box box, cbox; box.reset(); cbox.reset();
+        for(uint32_t i = job.first; i < job.first + job.count; ++i)
+        {
+            const HostPrim &p = prims[idx[i]];
+            box.grow(p.lo, p.hi);
+            cbox.grow_pt(&cen[3 * idx[i]]);
+        }
+        B2Node &nd = nodes[job.node];
+        nd.box = box; nd.left = nd.right = 0; nd.first = job.first; nd.count = job.count;
+        if(job.count <= 1) return false;
+
+        double best_cost = 1e300; int best_axis = -1, best_bin = -1;
+        double parent_area = box.area();
+        for(int axis = 0; axis < 3; ++axis)
+        {
+            float c0 = cbox.lo[axis], c1 = cbox.hi[axis];
+            if(!(c1 > c0)) continue;
+            Box bins[NBINS]; uint32_t cnt[NBINS];
+            for(int b = 0; b < NBINS; ++b) { bins[b].reset(); cnt[b] = 0; }
+            float scale = (float)NBINS / (c1 - c0);
+            for(uint32_t i = job.first; i < job.first + job.count; ++i)
+            {
+                uint32_t pi = idx[i];
+                int b = (int)((cen[3 * pi + axis] - c0) * scale);
+                if(b < 0) b = 0; if(b >= NBINS) b = NBINS - 1;
+                bins[b].grow(prims[pi].lo, prims[pi].hi); cnt[b]++;
+            }
+            double la[NBINS]; uint32_t ln[NBINS];
+            Box acc; acc.reset(); uint32_t c = 0;
+            for(int b = 0; b < NBINS - 1; ++b)
+            {
+                if(cnt[b]) acc.grow(bins[b].lo, bins[b].hi);
+                c += cnt[b]; la[b] = acc.area(); ln[b] = c;
+            }
+            acc.reset(); c = 0;
+            for(int b = NBINS - 1; b > 0; --b)
+            {
+                if(cnt[b]) acc.grow(bins[b].lo, bins[b].hi);
+                c += cnt[b];
+                if(ln[b - 1] == 0 || c == 0) continue;
+                double cost = la[b - 1] * ln[b - 1] + acc.area() * c;
+                if(cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            }
+        }
+        double leaf_cost = (double)job.count;
+        double split_cost = (best_axis >= 0 && parent_area > 0.0) ? opt.traversal_cost + best_cost / parent_area : 1e300;
+        if(job.count <= opt.max_leaf && leaf_cost <= split_cost) return false;   // leaf
+
+        uint32_t mid;
+        if(best_axis >= 0)
+        {
+            float c0 = cbox.lo[best_axis], c1 = cbox.hi[best_axis];
+            float scale = (float)NBINS / (c1 - c0);
+            uint32_t *b = &idx[job.first], *e = b + job.count;
+            int axis = best_axis, bin = best_bin;
+            uint32_t *m = std::partition(b, e, [&](uint32_t pi)
+            {
+                int bb = (int)((cen[3 * pi + axis] - c0) * scale);
+                if(bb < 0) bb = 0; if(bb >= NBINS) bb = NBINS - 1;
+                return bb < bin;
+            });
+            mid = (uint32_t)(m - &idx[0]);
+        }
+        else mid = job.first + job.count / 2;          // all centroids coincide: split the range in the middle
+        if(mid == job.first || mid == job.first + job.count) mid = job.first + job.count / 2;
+
+        uint32_t l = next_node.fetch_add(2);
+        nd.left = l; nd.right = l + 1; nd.count = 0;
+        *left = Job{ l, job.first, mid - job.first };
+        *right = Job{ l + 1, mid, job.first + job.count - mid };
+        return true;
+    }
+
+    // Top-down build; subtrees are independent (disjoint index ranges, nodes pre-allocated), so
+    // worker threads take them from a shared queue.  The tree does not depend on the schedule.
     void build()
     {
         size_t n = prims.size();
@@ -259,93 +344,58 @@ struct Builder
             idx[i] = (uint32_t)i;
             for(int k = 0; k < 3; ++k) cen[3 * i + k] = 0.5f * (prims[i].lo[k] + prims[i].hi[k]);
         }
-        nodes.reserve(2 * n + 1);
-        nodes.push_back(B2Node());
-        struct Job { uint32_t node, first, count; };
-        std::vector<Job> stack;
-        stack.push_back(Job{ 0u, 0u, (uint32_t)n });
-        const int NBINS = 16;
-        while(!stack.empty())
+        nodes.assign(2 * n + 1, B2Node());
+        std::atomic<uint32_t> next_node(1);
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<Job> queue;
+        size_t outstanding = 1;                 // jobs queued or being processed
+        queue.push_back(Job{ 0u, 0u, (uint32_t)n });
+        const uint32_t share_above = 32768;     // subtrees larger than this are offered to other threads
+        auto worker = [&]()
         {
-            Job job = stack.back(); stack.pop_back();
-            Box box, cbox; box.reset(); cbox.reset();
-            for(uint32_t i = job.first; i < job.first + job.count; ++i)
+            std::vector<Job> local;
+            for(;;)
             {
-                const HostPrim &p = prims[idx[i]];
-                box.grow(p.lo, p.hi);
-                cbox.grow_pt(&cen[3 * idx[i]]);
-            }
-            B2Node &nd = nodes[job.node];
-            nd.box = box; nd.left = nd.right = 0; nd.first = job.first; nd.count = job.count;
-            if(job.count <= 1) continue;
-
-            // best binned split
-            double best_cost = 1e300; int best_axis = -1, best_bin = -1;
-            double parent_area = box.area();
-            for(int axis = 0; axis < 3; ++axis)
-            {
-                float c0 = cbox.lo[axis], c1 = cbox.hi[axis];
-                if(!(c1 > c0)) continue;
-                Box bins[NBINS]; uint32_t cnt[NBINS];
-                for(int b = 0; b < NBINS; ++b) { bins[b].reset(); cnt[b] = 0; }
-                float scale = (float)NBINS / (c1 - c0);
-                for(uint32_t i = job.first; i < job.first + job.count; ++i)
+                Job job;
                 {
-                    uint32_t pi = idx[i];
-                    int b = (int)((cen[3 * pi + axis] - c0) * scale);
-                    if(b < 0) b = 0; if(b >= NBINS) b = NBINS - 1;
-                    bins[b].grow(prims[pi].lo, prims[pi].hi); cnt[b]++;
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return !queue.empty() || outstanding == 0; });
+                    if(queue.empty()) return;
+                    job = queue.back(); queue.pop_back();
                 }
-                double la[NBINS]; uint32_t ln[NBINS];
-                Box acc; acc.reset(); uint32_t c = 0;
-                for(int b = 0; b < NBINS - 1; ++b)
+                local.push_back(job);
+                while(!local.empty())
                 {
-                    if(cnt[b]) acc.grow(bins[b].lo, bins[b].hi);
-                    c += cnt[b]; la[b] = acc.area(); ln[b] = c;
+                    Job j = local.back(); local.pop_back();
+                    Job l, r;
+                    if(!split(j, next_node, &l, &r)) continue;
+                    Job small = l.count <= r.count ? l : r, big = l.count <= r.count ? r : l;
+                    local.push_back(small);
+                    if(big.count > share_above)
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        queue.push_back(big); ++outstanding;
+                        cv.notify_one();
+                    }
+                    else local.push_back(big);
                 }
-                acc.reset(); c = 0;
-                for(int b = NBINS - 1; b > 0; --b)
                 {
-                    if(cnt[b]) acc.grow(bins[b].lo, bins[b].hi);
-                    c += cnt[b];
-                    if(ln[b - 1] == 0 || c == 0) continue;
-                    double cost = la[b - 1] * ln[b - 1] + acc.area() * c;
-                    if(cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+                    std::lock_guard<std::mutex> lk(mu);
+                    --outstanding;
+                    if(outstanding == 0) cv.notify_all();
                 }
             }
-            double leaf_cost = (double)job.count;
-            double split_cost = (best_axis >= 0 && parent_area > 0.0) ? opt.traversal_cost + best_cost / parent_area : 1e300;
-            if(job.count <= opt.max_leaf && leaf_cost <= split_cost) continue;   // leaf
-
-            uint32_t mid;
-            if(best_axis >= 0)
-            {
-                float c0 = cbox.lo[best_axis], c1 = cbox.hi[best_axis];
-                float scale = (float)NBINS / (c1 - c0);
-                uint32_t *b = &idx[job.first], *e = b + job.count;
-                int axis = best_axis, bin = best_bin;
-                uint32_t *m = std::partition(b, e, [&](uint32_t pi)
-                {
-                    int bb = (int)((cen[3 * pi + axis] - c0) * scale);
-                    if(bb < 0) bb = 0; if(bb >= NBINS) bb = NBINS - 1;
-                    return bb < bin;
-                });
-                mid = (uint32_t)(m - &idx[0]);
-            }
-            else
-            {
-                // all centroids coincide: split the range in the middle
-                mid = job.first + job.count / 2;
-            }
-            if(mid == job.first || mid == job.first + job.count) mid = job.first + job.count / 2;
-
-            uint32_t l = (uint32_t)nodes.size();
-            nodes.push_back(B2Node()); nodes.push_back(B2Node());
-            B2Node &nd2 = nodes[job.node];   // re-fetch: push_back may have moved the storage
-            nd2.left = l; nd2.right = l + 1; nd2.count = 0;
-            stack.push_back(Job{ l + 1, mid, job.first + job.count - mid });
-            stack.push_back(Job{ l, job.first, mid - job.first });
-        }
+        };
+        unsigned nt = std::thread::hardware_concurrency();
+        if(nt == 0) nt = 1;
+        if(nt > 32) nt = 32;
+        if(n < 200000) nt = 1;
+        std::vector<std::thread> threads;
+        for(unsigned i = 1; i < nt; ++i) threads.emplace_back(worker);
+        worker();
+        for(auto &t : threads) t.join();
+        nodes.resize(next_node.load());
     }
 };
 
