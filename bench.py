@@ -249,7 +249,10 @@ def main_gpu(args):
     value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
 
     # kernel-only time and ray counts of one step (this rank), for the roofline
+    # (one pool for this pass: with two overlapping pools the per-stage event times overlap too)
+    os.environ["ORT_WF_POOLS"] = "1"
     st = scene.render_accumulate_device(hs.camera, P, accum.data_ptr(), stream=stream, want_stats=True)
+    del os.environ["ORT_WF_POOLS"]
     kernel_ms, rays, samples = st["device_ms"], st["rays"], st["samples"]
     # every kernel this library launches in one step (wavefront: extend/scan/scatter/shade per
     # iteration) + the resolve on rank 0

@@ -32,6 +32,23 @@ int fail(int code, const std::string &msg)
 
 } // namespace
 
+#define WF_BATCH 8
+#define WF_MAX_POOLS 2
+
+// A pool = a contiguous share of the slots with its own stream, sort scratch and counters.  Two
+// pools run the same loop half a period apart, so that one pool's SHADE (latency-bound) overlaps the
+// other's EXTEND (issue-bound) and every kernel's tail is filled by the other stream's blocks.
+struct WfPool
+{
+    WfBuffers wf;
+    uint32_t *d_sort;                       // hist[512] | cursor[512] | live | chunk counter
+    unsigned int *d_active, *h_active;      // 2 x WF_BATCH "slots still active" counters
+    cudaStream_t stream;
+    cudaEvent_t done[2], ev[2][WF_BATCH][4];
+    int cur;
+    bool finished;
+};
+
 struct OrtScene
 {
     int device;
@@ -52,14 +69,15 @@ struct OrtScene
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
     int wf_extend_blocks, wf_extend_q_blocks;
     uint32_t stack_rows;                // wide-tree depth + 1: rows of the shared-memory traversal stack
-    int wf_events_ready;
-    cudaEvent_t wf_done[2], wf_ev[2][8][4];
     float extend_ms, shade_ms, sort_ms; // summed stage times of the last wavefront render
-    // wavefront path pool
-    WfBuffers wf;
+    // wavefront path pool(s)
+    WfBuffers wf;                       // the whole allocation; pools[] view shares of it
     unsigned int *d_active;             // per-iteration "slots still active" counters
     unsigned int *h_active;             // pinned mirror
-    uint32_t *d_sort;                   // hist[512] | cursor[512] | live
+    uint32_t *d_sort;                   // per pool: hist[512] | cursor[512] | live | chunk counter
+    WfPool pools[WF_MAX_POOLS];
+    int wf_ready;
+    cudaEvent_t wf_start;
 
     SceneView view() const
     {
@@ -155,10 +173,30 @@ PathConsts make_consts(const OrtScene *s, const OrtCamera *cam, const OrtRenderP
     return c;
 }
 
-#define WF_BATCH 8
-
 int ensure_wavefront(OrtScene *s, uint32_t capacity)
 {
+    if(!s->wf_ready)
+    {
+        CUDA_TRY(cudaMalloc((void **)&s->d_sort, WF_MAX_POOLS * (2 * WF_KEY_BINS + 2) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc((void **)&s->d_active, WF_MAX_POOLS * 2 * WF_BATCH * sizeof(unsigned int)));
+        CUDA_TRY(cudaMallocHost((void **)&s->h_active, WF_MAX_POOLS * 2 * WF_BATCH * sizeof(unsigned int)));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->wf_start, cudaEventDisableTiming));
+        for(int p = 0; p < WF_MAX_POOLS; ++p)
+        {
+            WfPool &pl = s->pools[p];
+            CUDA_TRY(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
+            for(int b = 0; b < 2; ++b)
+            {
+                CUDA_TRY(cudaEventCreate(&pl.done[b]));
+                for(int it = 0; it < WF_BATCH; ++it)
+                    for(int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreate(&pl.ev[b][it][k]));
+            }
+            pl.d_sort = s->d_sort + p * (2 * WF_KEY_BINS + 2);
+            pl.d_active = s->d_active + p * 2 * WF_BATCH;
+            pl.h_active = s->h_active + p * 2 * WF_BATCH;
+        }
+        s->wf_ready = 1;
+    }
     if(s->wf.capacity >= capacity) return ORT_OK;
     cudaFree(s->wf.rec); cudaFree(s->wf.key); cudaFree(s->wf.perm);
     memset(&s->wf, 0, sizeof(s->wf));
@@ -166,149 +204,162 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
     CUDA_TRY(cudaMalloc((void **)&s->wf.key, (size_t)capacity * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.perm, (size_t)capacity * sizeof(uint32_t)));
     s->wf.capacity = capacity;
-    if(!s->d_active)
-    {
-        CUDA_TRY(cudaMalloc((void **)&s->d_sort, (2 * WF_KEY_BINS + 2) * sizeof(uint32_t)));
-        CUDA_TRY(cudaMalloc((void **)&s->d_active, 2 * WF_BATCH * sizeof(unsigned int)));
-        CUDA_TRY(cudaMallocHost((void **)&s->h_active, 2 * WF_BATCH * sizeof(unsigned int)));
-    }
     return ORT_OK;
 }
 
-// Wavefront driver: reset -> shade (generates the first rays) -> { extend -> shade }* until no
-// slot is active.  The "still active" count of every iteration is read back once per WF_BATCH
-// iterations, so the host never waits on a single launch.
+// Wavefront driver: per pool, reset -> shade (generates the first rays) -> { extend -> sort -> shade }*
+// until no slot of the pool is active.  The "still active" counts are read back once per WF_BATCH
+// iterations, one batch behind the enqueue, so the device never drains while the host decides.
 int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint32_t *launches)
 {
     uint32_t capacity = 1u << 22;      // 4 Mi slots x 104 B = 416 MB (measured: 1 Mi 636, 2 Mi 707, 4 Mi 720 Msamples/s at 1080p)
     if(const char *e = getenv("ORT_WF_SLOTS")) { long v = atol(e); if(v >= 1024 && v <= (1l << 26)) capacity = (uint32_t)v; }
     unsigned long long items128 = (a.total_items + 127ull) & ~127ull;
     if(items128 < capacity) capacity = (uint32_t)items128;
+    int n_pools = 2;
+    if(const char *e = getenv("ORT_WF_POOLS")) { int v = atoi(e); if(v >= 1 && v <= WF_MAX_POOLS) n_pools = v; }
+    if(capacity < (1u << 18)) n_pools = 1;
     int rc = ensure_wavefront(s, capacity);
     if(rc != ORT_OK) return rc;
-    WfBuffers wf = s->wf;
-    wf.capacity = capacity;
-    const unsigned grid = (capacity + 127u) / 128u;
     const int sorted = getenv("ORT_WF_NOSORT") ? 0 : 1;
     const size_t stack_bytes = (size_t)s->stack_rows * 128 * sizeof(uint2);
-    // persistent EXTEND grid: as many 4-warp blocks as stay resident, each warp owning a slot range
+    // persistent EXTEND grid: as many 4-warp blocks as stay resident
     if(s->wf_extend_blocks == 0)
     {
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend<false>, 128, s->stack_rows * 128 * sizeof(uint2)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend<false>, 128, stack_bytes));
         s->wf_extend_blocks = (nb > 0 ? nb : 1) * s->sm_count;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend_q<false>, 128, stack_bytes));
+        s->wf_extend_q_blocks = (nb > 0 ? nb : 1) * s->sm_count;
     }
-    unsigned egrid = (unsigned)s->wf_extend_blocks;
-    if(egrid > grid) egrid = grid;
-    uint32_t *hist = s->d_sort, *cursor = s->d_sort + WF_KEY_BINS, *live = s->d_sort + 2 * WF_KEY_BINS;
-    uint32_t *chunk_counter = s->d_sort + 2 * WF_KEY_BINS + 1;
     // 0 = k_wf_extend (default); 1 = k_wf_extend_q, the test-redistributing variant -- measured
     // slower on B200 (238 vs 202 ms of EXTEND per 1080p x 128 spp): rays wait for their queued tests
     const int extend_q = getenv("ORT_WF_EXTEND") ? atoi(getenv("ORT_WF_EXTEND")) : 0;
-    if(s->wf_extend_q_blocks == 0)
-    {
-        int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend_q<false>, 128, s->stack_rows * 128 * sizeof(uint2)));
-        s->wf_extend_q_blocks = (nb > 0 ? nb : 1) * s->sm_count;
-    }
-    unsigned qgrid = (unsigned)s->wf_extend_q_blocks;
-    if((unsigned long long)qgrid * 128ull > capacity) qgrid = (capacity + 127u) / 128u;
-    if(!s->wf_events_ready)
-    {
-        for(int b = 0; b < 2; ++b)
-        {
-            CUDA_TRY(cudaEventCreate(&s->wf_done[b]));
-            for(int it = 0; it < WF_BATCH; ++it)
-                for(int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreate(&s->wf_ev[b][it][k]));
-        }
-        s->wf_events_ready = 1;
-    }
+    const int extend_blocks_per_sm = getenv("ORT_WF_EXTEND_BPSM") ? atoi(getenv("ORT_WF_EXTEND_BPSM")) : 0;
     s->extend_ms = s->shade_ms = s->sort_ms = 0.f;
-    k_wf_reset<<<grid, 128, 0, stream>>>(wf);
-    CUDA_TRY(cudaMemsetAsync(s->d_active, 0, 2 * WF_BATCH * sizeof(unsigned int), stream));
-    k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, s->d_active, live, 0);
-    *launches += 2;
-    // Batches of WF_BATCH iterations are enqueued one ahead of the read-back of the previous
-    // batch's "still active" counters, so the device never drains while the host decides.
     const bool pipelined = a.total_items > 4ull * capacity;
-    auto enqueue = [&](int b) -> int
+
+    // the pools start after whatever the caller queued on its stream (e.g. zeroing the framebuffer)
+    CUDA_TRY(cudaEventRecord(s->wf_start, stream));
+    const uint32_t per_pool = ((capacity / (uint32_t)n_pools) + 127u) & ~127u;
+    for(int p = 0; p < n_pools; ++p)
     {
-        unsigned int *act = s->d_active + b * WF_BATCH;
-        CUDA_TRY(cudaMemsetAsync(act, 0, WF_BATCH * sizeof(unsigned int), stream));
+        WfPool &pl = s->pools[p];
+        uint32_t lo = (uint32_t)p * per_pool, hi = lo + per_pool;
+        if(hi > capacity || p == n_pools - 1) hi = capacity;
+        if(lo > hi) lo = hi;
+        pl.wf.rec = s->wf.rec + (size_t)WF_REC_QUADS * lo;
+        pl.wf.key = s->wf.key + lo;
+        pl.wf.perm = s->wf.perm + lo;
+        pl.wf.capacity = hi - lo;
+        pl.cur = 0; pl.finished = pl.wf.capacity == 0;
+        CUDA_TRY(cudaStreamWaitEvent(pl.stream, s->wf_start, 0));
+    }
+
+    auto enqueue = [&](WfPool &pl, int b) -> int
+    {
+        const uint32_t cap = pl.wf.capacity;
+        const unsigned grid = (cap + 127u) / 128u;
+        unsigned egrid = (unsigned)(extend_q ? s->wf_extend_q_blocks : s->wf_extend_blocks);
+        if(extend_blocks_per_sm > 0 && (unsigned)(extend_blocks_per_sm * s->sm_count) < egrid) egrid = (unsigned)(extend_blocks_per_sm * s->sm_count);
+        if(egrid > grid) egrid = grid;
+        uint32_t *hist = pl.d_sort, *cursor = pl.d_sort + WF_KEY_BINS, *live = pl.d_sort + 2 * WF_KEY_BINS;
+        uint32_t *chunk_counter = pl.d_sort + 2 * WF_KEY_BINS + 1;
+        unsigned int *act = pl.d_active + b * WF_BATCH;
+        cudaStream_t st = pl.stream;
+        CUDA_TRY(cudaMemsetAsync(act, 0, WF_BATCH * sizeof(unsigned int), st));
         for(int it = 0; it < WF_BATCH; ++it)
         {
-            CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), stream));
-            CUDA_TRY(cudaMemsetAsync(chunk_counter, 0, sizeof(uint32_t), stream));
-            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][0], stream));
+            CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), st));
+            CUDA_TRY(cudaMemsetAsync(chunk_counter, 0, sizeof(uint32_t), st));
+            CUDA_TRY(cudaEventRecord(pl.ev[b][it][0], st));
             if(extend_q)
             {
 #ifdef ORT_COUNTERS
-                k_wf_extend_q<true><<<qgrid, 128, stack_bytes, stream>>>(a.scene, wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
+                k_wf_extend_q<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
 #else
-                k_wf_extend_q<false><<<qgrid, 128, stack_bytes, stream>>>(a.scene, wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
+                k_wf_extend_q<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
 #endif
             }
             else
             {
 #ifdef ORT_COUNTERS
-                k_wf_extend<true><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, chunk_counter, a.stats, hist);
+                k_wf_extend<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
 #else
-                k_wf_extend<false><<<egrid, 128, stack_bytes, stream>>>(a.scene, wf, chunk_counter, a.stats, hist);
+                k_wf_extend<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
 #endif
             }
-            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][1], stream));
+            CUDA_TRY(cudaEventRecord(pl.ev[b][it][1], st));
             if(sorted)
             {
-                k_wf_scan<<<1, WF_KEY_BINS, 0, stream>>>(hist, cursor, live);
-                k_wf_scatter<<<(capacity + 1023u) / 1024u, 1024, 0, stream>>>(wf, cursor);
+                k_wf_scan<<<1, WF_KEY_BINS, 0, st>>>(hist, cursor, live);
+                k_wf_scatter<<<(cap + 1023u) / 1024u, 1024, 0, st>>>(pl.wf, cursor);
                 *launches += 2;
             }
-            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][2], stream));
-            k_wf_shade<<<grid, 128, 0, stream>>>(a, wf, act + it, live, sorted);
-            CUDA_TRY(cudaEventRecord(s->wf_ev[b][it][3], stream));
+            CUDA_TRY(cudaEventRecord(pl.ev[b][it][2], st));
+            k_wf_shade<<<grid, 128, 0, st>>>(a, pl.wf, act + it, live, sorted);
+            CUDA_TRY(cudaEventRecord(pl.ev[b][it][3], st));
         }
         *launches += 2 * WF_BATCH;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(s->h_active + b * WF_BATCH, act, WF_BATCH * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaEventRecord(s->wf_done[b], stream));
+        CUDA_TRY(cudaMemcpyAsync(pl.h_active + b * WF_BATCH, act, WF_BATCH * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(pl.done[b], st));
         return ORT_OK;
     };
-    auto collect = [&](int b, bool *finished) -> int
+    auto collect = [&](WfPool &pl, int b, bool *finished) -> int
     {
-        CUDA_TRY(cudaEventSynchronize(s->wf_done[b]));
+        CUDA_TRY(cudaEventSynchronize(pl.done[b]));
         for(int it = 0; it < WF_BATCH; ++it)
         {
             float e = 0.f, so = 0.f, sh = 0.f;
-            cudaEventElapsedTime(&e, s->wf_ev[b][it][0], s->wf_ev[b][it][1]);
-            cudaEventElapsedTime(&so, s->wf_ev[b][it][1], s->wf_ev[b][it][2]);
-            cudaEventElapsedTime(&sh, s->wf_ev[b][it][2], s->wf_ev[b][it][3]);
+            cudaEventElapsedTime(&e, pl.ev[b][it][0], pl.ev[b][it][1]);
+            cudaEventElapsedTime(&so, pl.ev[b][it][1], pl.ev[b][it][2]);
+            cudaEventElapsedTime(&sh, pl.ev[b][it][2], pl.ev[b][it][3]);
             s->extend_ms += e; s->sort_ms += so; s->shade_ms += sh;
         }
-        *finished = s->h_active[b * WF_BATCH + WF_BATCH - 1] == 0;
+        *finished = pl.h_active[b * WF_BATCH + WF_BATCH - 1] == 0;
         return ORT_OK;
     };
-    int cur = 0;
-    bool finished = false;
-    rc = enqueue(cur);
-    if(rc != ORT_OK) return rc;
-    while(!finished)
+
+    for(int p = 0; p < n_pools; ++p)
     {
-        if(pipelined)
-        {
-            rc = enqueue(cur ^ 1);
-            if(rc != ORT_OK) return rc;
-            rc = collect(cur, &finished);
-            if(rc != ORT_OK) return rc;
-            cur ^= 1;
-            if(finished) { bool dummy; rc = collect(cur, &dummy); if(rc != ORT_OK) return rc; }
-        }
-        else
-        {
-            rc = collect(cur, &finished);
-            if(rc != ORT_OK) return rc;
-            if(!finished) { rc = enqueue(cur); if(rc != ORT_OK) return rc; }
-        }
+        WfPool &pl = s->pools[p];
+        if(pl.finished) continue;
+        const unsigned grid = (pl.wf.capacity + 127u) / 128u;
+        k_wf_reset<<<grid, 128, 0, pl.stream>>>(pl.wf);
+        CUDA_TRY(cudaMemsetAsync(pl.d_active, 0, 2 * WF_BATCH * sizeof(unsigned int), pl.stream));
+        k_wf_shade<<<grid, 128, 0, pl.stream>>>(a, pl.wf, pl.d_active, pl.d_sort + 2 * WF_KEY_BINS, 0);
+        *launches += 2;
+        rc = enqueue(pl, 0);
+        if(rc != ORT_OK) return rc;
     }
+    for(;;)
+    {
+        bool any = false;
+        for(int p = 0; p < n_pools; ++p)
+        {
+            WfPool &pl = s->pools[p];
+            if(pl.finished) continue;
+            any = true;
+            if(pipelined)
+            {
+                rc = enqueue(pl, pl.cur ^ 1);
+                if(rc != ORT_OK) return rc;
+                rc = collect(pl, pl.cur, &pl.finished);
+                if(rc != ORT_OK) return rc;
+                pl.cur ^= 1;
+                if(pl.finished) { bool dummy; rc = collect(pl, pl.cur, &dummy); if(rc != ORT_OK) return rc; }
+            }
+            else
+            {
+                rc = collect(pl, pl.cur, &pl.finished);
+                if(rc != ORT_OK) return rc;
+                if(!pl.finished) { rc = enqueue(pl, pl.cur); if(rc != ORT_OK) return rc; }
+            }
+        }
+        if(!any) break;
+    }
+    for(int p = 0; p < n_pools; ++p) CUDA_TRY(cudaStreamSynchronize(s->pools[p].stream));
     return ORT_OK;
 }
 
@@ -480,6 +531,19 @@ int ort_scene_destroy(OrtScene *s)
     cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_cyl); cudaFree(s->d_materials);
     cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb);
     cudaFree(s->wf.rec); cudaFree(s->d_active);
+    if(s->wf_ready)
+    {
+        cudaEventDestroy(s->wf_start);
+        for(int p = 0; p < WF_MAX_POOLS; ++p)
+        {
+            cudaStreamDestroy(s->pools[p].stream);
+            for(int b = 0; b < 2; ++b)
+            {
+                cudaEventDestroy(s->pools[p].done[b]);
+                for(int it = 0; it < WF_BATCH; ++it) for(int k = 0; k < 4; ++k) cudaEventDestroy(s->pools[p].ev[b][it][k]);
+            }
+        }
+    }
     cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->d_sort);
     if(s->h_active) cudaFreeHost(s->h_active);
     if(s->ev0) cudaEventDestroy(s->ev0);
