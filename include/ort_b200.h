@@ -52,6 +52,10 @@ int ort_device_count(int *count);
  * FMUL+FADD kernel (no FMA contraction -- the instruction mix of the intersectors).
  * MEASURED_PEAKS.json carries no FP32 figure.  The third argument is unused. */
 int ort_measure_fp32_peak(int device, float *tflops_non_fma, float *reserved);
+/* Self-test of the device's shared-reciprocal vector division (csrc/core_math.h, div3_shared: the
+ * three quotients of math.h:235 `v3 / f32` as used by `normalize`, math.h:299) against the
+ * compiler's IEEE-754 division on `triples` random operand sets; *mismatches must come back 0. */
+int ort_selftest_div3(int device, uint64_t triples, uint32_t seed, uint64_t *tested, uint64_t *mismatches);
 
 /* ------------------------------------------------------------------------
  * Scene hand-off.

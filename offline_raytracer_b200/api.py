@@ -149,6 +149,15 @@ def measure_fp32_peak(device=0):
     return float(v.value)
 
 
+def selftest_div3(triples=1 << 28, seed=12345, device=0):
+    """(tested, mismatches) of the shared-reciprocal division self-test; mismatches must be 0"""
+    L = lib()
+    L.ort_selftest_div3.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    t, m = C.c_uint64(0), C.c_uint64(0)
+    _check(L.ort_selftest_div3(device, triples, seed, C.byref(t), C.byref(m)))
+    return int(t.value), int(m.value)
+
+
 def default_params(width, height, spp, rr=0.8, seed=1234567, chunk_spp=0, kernel=ORT_KERNEL_DEFAULT):
     p = RenderParams()
     lib().ort_render_params_default(C.byref(p), width, height, spp)

@@ -52,7 +52,7 @@ struct alignas(16) WideNode
 {
     float px, py, pz;
     uint8_t ex, ey, ez, imask;
-    uint32_t child_base, prim_base;
+    uint32_t child_base, prim_base;       // prim_base bit 31 (ORT_NODE_MIXED_KINDS): some leaf record of the node is not a triangle
     uint8_t meta[8];
     uint8_t qlo_x[8], qlo_y[8];
     uint8_t qlo_z[8], qhi_x[8];
@@ -68,6 +68,7 @@ struct alignas(16) PrimRec
 };
 static_assert(sizeof(PrimRec) == 48, "PrimRec is 3 x 16 B");
 
+#define ORT_NODE_MIXED_KINDS 0x80000000u
 enum { PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_AAB = 2, PRIM_CYLINDER = 3 };
 
 struct alignas(16) CylinderAux
@@ -203,7 +204,7 @@ ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
 // applies: nodes below main_root -- the sphere tree -- are never clipped).
 template <bool COUNT, class Stack>
 ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, TraceCounters *cnt,
-                       uint32_t *tg_x_out, uint32_t *tg_y_out, uint32_t *node_index_out)
+                       uint32_t *tg_x_out, uint32_t *tg_y_out, uint32_t *node_index_out, uint32_t *mixed_out = 0)
 {
     // reciprocal direction of the (conservative) slab tests: the exact one, except that zero and
     // denormal-small components are clamped so that 0 * inf never appears
@@ -277,7 +278,8 @@ ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, Tra
         }
     }
     t.ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);
-    *tg_x_out = f2u(n1.y);
+    *tg_x_out = f2u(n1.y) & ~ORT_NODE_MIXED_KINDS;
+    if(mixed_out) *mixed_out = f2u(n1.y) >> 31;
     *tg_y_out = hitmask & 0x00FFFFFFu;
     *node_index_out = node_index;
 }

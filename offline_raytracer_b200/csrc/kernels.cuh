@@ -273,6 +273,47 @@ k_fp32_peak(float *out, int iters, float b, float c)
     if(s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;      // never true; keeps the chains alive
 }
 
+// Self-test of core_math.h's div3_shared (three IEEE quotients from one reciprocal) against the
+// compiler's own division: each thread draws `iters` random (x, y, z, s) -- random sign and mantissa,
+// exponent uniform in a window that straddles the fast path's range guard, and now and then a
+// zero, a subnormal, an infinity or a NaN -- and counts the quotients whose bits differ.
+__device__ __forceinline__ uint32_t st_next(uint32_t &x) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; }
+__device__ __forceinline__ float st_float(uint32_t &x)
+{
+    uint32_t r = st_next(x), m = st_next(x);
+    uint32_t special = (r >> 16) & 63u;
+    if(special == 0u) return __uint_as_float(r & 0x80000000u);                      // +-0
+    if(special == 1u) return __uint_as_float((r & 0x80000000u) | (m & 0x007FFFFFu)); // subnormal
+    if(special == 2u) return __uint_as_float((r & 0x80000000u) | 0x7F800000u);       // +-inf
+    if(special == 3u) return __uint_as_float(0x7FC00000u | (m & 0x3FFFFFu));         // NaN
+    uint32_t e = 127u - 70u + (r & 0xFFFFu) % 141u;                                  // 2^-70 .. 2^70
+    return __uint_as_float((r & 0x80000000u) | (e << 23) | (m & 0x007FFFFFu));
+}
+__global__ void __launch_bounds__(256)
+k_selftest_div3(uint32_t seed, int iters, unsigned long long *mismatches)
+{
+    uint32_t x = seed ^ ((blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u);
+    if(x == 0u) x = 1u;
+    unsigned int bad = 0;
+    for(int i = 0; i < iters; ++i)
+    {
+        f3 a = mk3(st_float(x), st_float(x), st_float(x));
+        float s = st_float(x);
+        f3 q = div3_shared(a, s);
+        float rx = a.x / s, ry = a.y / s, rz = a.z / s;
+        // NaNs compare as "both NaN": payloads of invalid operations are not part of the contract
+        bad += ((q.x != q.x) && (rx != rx)) ? 0u : (__float_as_uint(q.x) != __float_as_uint(rx));
+        bad += ((q.y != q.y) && (ry != ry)) ? 0u : (__float_as_uint(q.y) != __float_as_uint(ry));
+        bad += ((q.z != q.z) && (rz != rz)) ? 0u : (__float_as_uint(q.z) != __float_as_uint(rz));
+#ifdef ORT_SELFTEST_PRINT
+        if(!((q.x != q.x) && (rx != rx)) && __float_as_uint(q.x) != __float_as_uint(rx) && atomicAdd(mismatches + 1, 1ull) < 12ull)
+            printf("x %08x s %08x got %08x want %08x\n", __float_as_uint(a.x), __float_as_uint(s), __float_as_uint(q.x), __float_as_uint(rx));
+#endif
+    }
+    bad = __reduce_add_sync(0xFFFFFFFFu, bad);
+    if((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
 __global__ void k_zero_u64(unsigned long long *p, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -260,7 +260,7 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     {
         const uint32_t cap = pl.wf.capacity;
         const unsigned grid = (cap + 127u) / 128u;
-        unsigned egrid = (unsigned)(extend_q ? s->wf_extend_q_blocks : s->wf_extend_blocks);
+        unsigned egrid = (unsigned)(extend_q == 1 ? s->wf_extend_q_blocks : s->wf_extend_blocks);
         if(extend_blocks_per_sm > 0 && (unsigned)(extend_blocks_per_sm * s->sm_count) < egrid) egrid = (unsigned)(extend_blocks_per_sm * s->sm_count);
         if(egrid > grid) egrid = grid;
         uint32_t *hist = pl.d_sort, *cursor = pl.d_sort + WF_KEY_BINS, *live = pl.d_sort + 2 * WF_KEY_BINS;
@@ -273,7 +273,15 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
             CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), st));
             CUDA_TRY(cudaMemsetAsync(chunk_counter, 0, sizeof(uint32_t), st));
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][0], st));
-            if(extend_q)
+            if(extend_q == 2)
+            {
+#ifdef ORT_COUNTERS
+                k_wf_extend_v<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
+#else
+                k_wf_extend_v<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
+#endif
+            }
+            else if(extend_q)
             {
 #ifdef ORT_COUNTERS
                 k_wf_extend_q<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
@@ -437,6 +445,30 @@ int ort_device_count(int *count)
     cudaError_t e = cudaGetDeviceCount(&n);
     if(count) *count = (e == cudaSuccess) ? n : 0;
     if(e != cudaSuccess || n == 0) return fail(ORT_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return ORT_OK;
+}
+
+int ort_selftest_div3(int device, uint64_t triples, uint32_t seed, uint64_t *tested, uint64_t *mismatches)
+{
+    if(!tested || !mismatches) return fail(ORT_ERR_ARG, "null argument");
+    int n = 0;
+    if(ort_device_count(&n) != ORT_OK) return ORT_ERR_CUDA;
+    if(device < 0 || device >= n) return fail(ORT_ERR_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    const int blocks = 148 * 8, threads = 256;
+    uint64_t per_thread = (triples + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
+    if(per_thread == 0) per_thread = 1;
+    if(per_thread > (1u << 24)) return fail(ORT_ERR_ARG, "too many triples for one launch");
+    unsigned long long *d_bad = 0;
+    CUDA_TRY(cudaMalloc((void **)&d_bad, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d_bad, 0, 2 * sizeof(unsigned long long)));
+    k_selftest_div3<<<blocks, threads>>>(seed, (int)per_thread, d_bad);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long bad = 0;
+    CUDA_TRY(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    *tested = per_thread * (uint64_t)blocks * threads;
+    *mismatches = bad;
     return ORT_OK;
 }
 

@@ -79,7 +79,7 @@ struct PathConsts
     int32_t width, height;
     uint32_t light_count;
     const uint8_t *light_is_sphere;    // one byte per light-list entry
-    const q4 *materials;               // DevMaterial[] viewed as q4[4*n]
+    const q4 *materials;               // DevMaterial[] viewed as q4[6*n]
 };
 
 struct Mat
@@ -87,16 +87,24 @@ struct Mat
     f3 Kd, Ks, Kt, emit;
     float ior;
     int is_light;
+    // per-material constants formed once by the flattener (scene_flatten.h, DevMaterial) with the
+    // operations of ray.cpp:1013-1019 / 940 -- the values pdf_brdf, sample_brdf and
+    // eval_scattering would otherwise recompute at every bounce
+    float pd_c, ps_c, pt_c;
+    f3 Ed;
+    uint32_t lobes;                    // bit 0/1/2: length_square(Kd/Ks/Kt) > 0
 };
 ORT_HD Mat load_material(const PathConsts &c, uint32_t index)
 {
-    const q4 *p = c.materials + 4u * index;
-    q4 a = ldq(p), b = ldq(p + 1), t = ldq(p + 2), e = ldq(p + 3);
+    const q4 *p = c.materials + 6u * index;
+    q4 a = ldq(p), b = ldq(p + 1), t = ldq(p + 2), e = ldq(p + 3), k = ldq(p + 4), d = ldq(p + 5);
     Mat m;
     m.Kd = q3(a); m.is_light = (int)f2u(a.w);
     m.Ks = q3(b); m.ior = b.w;
-    m.Kt = q3(t);
+    m.Kt = q3(t); m.lobes = f2u(t.w);
     m.emit = q3(e);
+    m.pd_c = k.x; m.ps_c = k.y; m.pt_c = k.z;
+    m.Ed = q3(d);
     return m;
 }
 
@@ -192,15 +200,28 @@ ORT_HD Beern get_beer_n(f3 N, f3 wo, float ior)                          // ray.
     return r;
 }
 
-ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, f3 Kd, f3 Ks, f3 Kt, float ior, float roughness, float distance)   // ray.cpp:936-1005
+// The half vector H and the refraction half vector m are only formed for materials whose
+// specular / transmission lobe can use them (the reference computes them unconditionally and then
+// leaves them unused: ray.cpp:943-951, 1027-1030, 1041-1047) -- a diffuse surface, i.e. most
+// bounces, skips two normalisations per call.  Every value that reaches the result is computed
+// exactly as before.
+ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, const Mat &mt, float roughness, float distance)   // ray.cpp:936-1005
 {
-    f3 Ed = Kd / ORT_PI_32;
-    f3 H = ref_sign(dot(wi, N)) * nrm(wo + wi);
-    float wi_dot_h = dot(wi, H);
+    const f3 Ks = mt.Ks, Kt = mt.Kt;
+    const float ior = mt.ior;
+    f3 Ed = mt.Ed;
     f3 Es = mk3(0.0f, 0.0f, 0.0f);
     float wi_dot_n = dot(wi, N);
     float wo_dot_n = dot(wo, N);
-    if(wi_dot_h > 0.0f && length_square(Ks) > 0.0f)
+    const bool has_Ks = (mt.lobes & 2u) != 0u, has_Kt = (mt.lobes & 4u) != 0u;
+    f3 H = mk3(0.0f, 0.0f, 0.0f);
+    float wi_dot_h = 0.0f;
+    if(has_Ks)
+    {
+        H = ref_sign(dot(wi, N)) * nrm(wo + wi);
+        wi_dot_h = dot(wi, H);
+    }
+    if(has_Ks && wi_dot_h > 0.0f)
     {
         f3 F = fresnel(Ks, wi_dot_h);
         float D = ggx_distribution(N, H, roughness);
@@ -208,7 +229,7 @@ ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, f3 Kd, f3 Ks, f3 Kt, float ior, fl
         Es = ((D * G) / (4.0f * absolute(wi_dot_n) * absolute(wo_dot_n))) * F;
     }
     f3 Et = mk3(0.0f, 0.0f, 0.0f);
-    if(length_square(Kt) > 0.0f)
+    if(has_Kt)
     {
         f3 At = mk3(1.0f, 1.0f, 1.0f);
         if(wo_dot_n < 0)
@@ -222,7 +243,7 @@ ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, f3 Kd, f3 Ks, f3 Kt, float ior, fl
         float r = get_radicand(m, wo, bn.n);
         if(r < 0.0f)
         {
-            if(length_square(Ks) > 0.0f) Et = hadamard(At, Es);     // total internal reflection
+            if(has_Ks) Et = hadamard(At, Es);     // total internal reflection
         }
         else
         {
@@ -242,18 +263,16 @@ ORT_HD f3 eval_scattering(f3 N, f3 wi, f3 wo, f3 Kd, f3 Ks, f3 Kt, float ior, fl
     return absolute(wi_dot_n) * (Ed + Es + Et);
 }
 
-ORT_HD float pdf_brdf(f3 N, f3 wi, f3 wo, float roughness, f3 Kd, f3 Ks, f3 Kt, float ior)   // ray.cpp:1007-1063
+ORT_HD float pdf_brdf(f3 N, f3 wi, f3 wo, float roughness, const Mat &mt)   // ray.cpp:1007-1063
 {
-    float Kd_l = length(Kd), Ks_l = length(Ks), Kt_l = length(Kt);
-    float s = Kd_l + Ks_l + Kt_l;
-    float pd_c = Kd_l / s, ps_c = Ks_l / s, pt_c = Kt_l / s;
+    const float pd_c = mt.pd_c, ps_c = mt.ps_c, pt_c = mt.pt_c, ior = mt.ior;
     float pd = absolute(dot(wi, N)) / ORT_PI_32;
-    f3 H = ref_sign(dot(N, wi)) * nrm(wo + wi);
-    float n_dot_h = dot(N, H);
-    float wi_dot_h = dot(wi, H);
     float ps = 0.0f;
     if(ps_c > 0.0f)
     {
+        f3 H = ref_sign(dot(N, wi)) * nrm(wo + wi);
+        float n_dot_h = dot(N, H);
+        float wi_dot_h = dot(wi, H);
         float denom = (4.0f * absolute(wi_dot_h));
         if(!compare_equal_f32(denom, 0.0f))
         {
@@ -261,12 +280,14 @@ ORT_HD float pdf_brdf(f3 N, f3 wi, f3 wo, float roughness, f3 Kd, f3 Ks, f3 Kt, 
             ps = D * absolute(n_dot_h) / denom;
         }
     }
-    Beern bn = get_beer_n(N, wo, ior);
-    f3 m = nrm(-(bn.ni * wi + bn.no * wo));
-    float r = get_radicand(m, wo, bn.n);
     float pt = ps;                                                       // sic, ray.cpp:1046
-    if(pt_c > 0.0f && r >= 0.0f)
+    if(pt_c > 0.0f)
     {
+      Beern bn = get_beer_n(N, wo, ior);
+      f3 m = nrm(-(bn.ni * wi + bn.no * wo));
+      float r = get_radicand(m, wo, bn.n);
+      if(r >= 0.0f)
+      {
         float n_dot_m = dot(N, m);
         float wi_dot_m = dot(wi, m);
         float wo_dot_m = dot(wo, m);
@@ -276,6 +297,7 @@ ORT_HD float pdf_brdf(f3 N, f3 wi, f3 wo, float roughness, f3 Kd, f3 Ks, f3 Kt, 
             float D = ggx_distribution(N, m, roughness);
             pt = D * absolute(n_dot_m) * square(bn.no) * absolute(wi_dot_m) / denom;
         }
+      }
     }
     return pd_c * pd + ps_c * ps + pt_c * pt;
 }
@@ -293,12 +315,10 @@ ORT_HD_BIG f3 sample_lobe(f3 N, float c, float phi)                          // 
 }
 
 struct SampleBRDF { f3 wi; int is_transmission; };
-ORT_HD SampleBRDF sample_brdf(uint32_t *series, f3 N, f3 wo, float roughness, f3 Kd, f3 Ks, f3 Kt, float ior)   // ray.cpp:1100-1161
+ORT_HD SampleBRDF sample_brdf(uint32_t *series, f3 N, f3 wo, float roughness, const Mat &mt)   // ray.cpp:1100-1161
 {
     SampleBRDF res; res.wi = mk3(0.0f, 0.0f, 0.0f); res.is_transmission = 0;
-    float Kd_l = length(Kd), Ks_l = length(Ks), Kt_l = length(Kt);
-    float s = Kd_l + Ks_l + Kt_l;
-    float pd_c = Kd_l / s, ps_c = Ks_l / s;
+    const float pd_c = mt.pd_c, ps_c = mt.ps_c, ior = mt.ior;
     float e0 = random_between_0_1(series);
     float e1 = random_between_0_1(series);
     float choice = random_between_0_1(series);
@@ -381,7 +401,7 @@ ORT_HD bool shade_primary(const PathConsts &c, Path *p, float hit_t, uint32_t hi
     p->origin = p->origin + (hit_t - c.eps) * p->dir;                    // ray.cpp:1262
     p->normal = hit_normal;
     p->mat = hit_mat;
-    if(length_square(m.Kd) > 0.0f) p->weight = hadamard(p->weight, m.Kd);
+    if(m.lobes & 1u) p->weight = hadamard(p->weight, m.Kd);
     return true;
 }
 
@@ -392,7 +412,7 @@ ORT_HD bool next_bounce(const PathConsts &c, Path *p)
     if(!(random_between_0_1(&p->series) < c.rr)) return false;
     sample_random_lights_rng(c, &p->series);
     Mat m = load_material(c, p->mat);
-    SampleBRDF sb = sample_brdf(&p->series, p->normal, p->wo, c.roughness, m.Kd, m.Ks, m.Kt, m.ior);
+    SampleBRDF sb = sample_brdf(&p->series, p->normal, p->wo, c.roughness, m);
     if(sb.is_transmission) p->origin = p->origin + (2.0f * c.eps) * p->dir;   // p->dir is still previous_ray_dir
     p->dir = sb.wi;
     return true;
@@ -410,10 +430,10 @@ ORT_HD bool shade_bounce(const PathConsts &c, Path *p, float hit_t, uint32_t hit
         return false;
     }
     f3 wi = p->dir;
-    float pdf = pdf_brdf(hit_normal, wi, p->wo, c.roughness, m.Kd, m.Ks, m.Kt, m.ior) * c.rr;   // ray.cpp:1380
+    float pdf = pdf_brdf(hit_normal, wi, p->wo, c.roughness, m) * c.rr;   // ray.cpp:1380
     if(pdf > 0.000001f)
     {
-        f3 f = eval_scattering(hit_normal, wi, p->wo, m.Kd, m.Ks, m.Kt, m.ior, c.roughness, hit_t);
+        f3 f = eval_scattering(hit_normal, wi, p->wo, m, c.roughness, hit_t);
         p->weight = hadamard(f / pdf, p->weight);                        // ray.cpp:1403
     }
     p->origin = p->origin + (hit_t - c.eps) * wi;                        // ray.cpp:1411

@@ -92,6 +92,21 @@ void prim_bounds(HostPrim &p)
 
 } // namespace
 
+// the per-material constants of DevMaterial, exactly as path.h's pdf_brdf / sample_brdf /
+// eval_scattering form them (float arithmetic, this file is compiled with -ffp-contract=off)
+static void material_constants(DevMaterial *dm)
+{
+    f3 Kd = mk3(dm->diffuse[0], dm->diffuse[1], dm->diffuse[2]);
+    f3 Ks = mk3(dm->specular[0], dm->specular[1], dm->specular[2]);
+    f3 Kt = mk3(dm->transmission[0], dm->transmission[1], dm->transmission[2]);
+    float Kd_l = length(Kd), Ks_l = length(Ks), Kt_l = length(Kt);
+    float s = Kd_l + Ks_l + Kt_l;
+    dm->pd_c = Kd_l / s; dm->ps_c = Ks_l / s; dm->pt_c = Kt_l / s;
+    f3 Ed = Kd / ORT_PI_32;
+    dm->ed[0] = Ed.x; dm->ed[1] = Ed.y; dm->ed[2] = Ed.z;
+    dm->lobes = (length_square(Kd) > 0.0f ? 1u : 0u) | (length_square(Ks) > 0.0f ? 2u : 0u) | (length_square(Kt) > 0.0f ? 4u : 0u);
+}
+
 int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
                     std::vector<HostPrim> *prims, FlatScene *out, std::string *err)
 {
@@ -195,6 +210,7 @@ int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
         dm.emit[0] = m.emit_color.x; dm.emit[1] = m.emit_color.y; dm.emit[2] = m.emit_color.z;
         dm.ior = m.ior;
         dm.is_light = m.is_light;
+        material_constants(&dm);
     }
     out->info.material_count = world->mat_count;
 
@@ -528,6 +544,7 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
         n.child_base = (uint32_t)out->nodes.size();
         n.prim_base = (uint32_t)out->prims.size();
         uint32_t prim_off = 0;
+        bool only_triangles = true;
         for(int s = 0; s < 8; ++s)
         {
             if(kid_at[s] < 0) continue;
@@ -547,6 +564,7 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
                 for(uint32_t i = 0; i < c.count; ++i)
                 {
                     const HostPrim &hp = prims[b.idx[c.first + i]];
+                    if(hp.kind != PRIM_TRIANGLE) only_triangles = false;
                     PrimRec r; memset(&r, 0, sizeof(r));
                     r.rank = hp.rank; r.mat = hp.mat;
                     r.ax = hp.a.x; r.ay = hp.a.y; r.az = hp.a.z;
@@ -583,6 +601,8 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
                 prim_off += c.count;
             }
         }
+        if(n.prim_base >= ORT_NODE_MIXED_KINDS) { *err = "too many primitive records"; return ORT_ERR_LIMIT; }
+        if(!only_triangles) n.prim_base |= ORT_NODE_MIXED_KINDS;
         out->nodes[self] = n;
     }
 

@@ -22,15 +22,21 @@ struct HostPrim
     float lo[3], hi[3]; // conservative, padded bounds
 };
 
-// device material, 64 B = 4 x 16 B (OrtMaterial re-packed for 128-bit loads)
+// device material, 96 B = 6 x 16 B: OrtMaterial re-packed for 128-bit loads, plus the per-material
+// constants that pdf_brdf / sample_brdf / eval_scattering (ray.cpp:1007-1161, 936-1005) would
+// otherwise re-derive at every bounce -- six square roots and eight divisions.  They are formed
+// here with the same IEEE single-precision operations in the same order (no contraction), so the
+// device reads the very bits it would have computed.
 struct alignas(16) DevMaterial
 {
     float diffuse[3];      int32_t is_light;
     float specular[3];     float ior;
-    float transmission[3]; float pad0;
+    float transmission[3]; uint32_t lobes;    // bit 0/1/2: length_square(Kd/Ks/Kt) > 0
     float emit[3];         float pad1;
+    float pd_c, ps_c, pt_c, pad2;             // |Kd|/s, |Ks|/s, |Kt|/s with s = |Kd|+|Ks|+|Kt| (ray.cpp:1013-1019)
+    float ed[3];           float pad3;        // Kd / pi (ray.cpp:940)
 };
-static_assert(sizeof(DevMaterial) == 64, "DevMaterial is 4 x 16 B");
+static_assert(sizeof(DevMaterial) == 96, "DevMaterial is 6 x 16 B");
 
 struct BuildOptions
 {

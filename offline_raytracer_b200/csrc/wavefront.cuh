@@ -63,6 +63,16 @@ struct SharedStack
     __device__ __forceinline__ void get(int i, uint32_t &a, uint32_t &b) const { uint2 v = col[i * 128]; a = v.x; b = v.y; }
 };
 
+// EXTEND's result: q5.xy = (t, primitive)
+// (tried, B200: also storing the material here and loading the whole record + material up front in
+//  SHADE, to shorten its chain of dependent loads -- SHADE 133.1 vs 130.7 ms, the extra live registers
+//  cost more than the shorter chain saves)
+__device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot, float t, uint32_t prim, uint32_t mat)
+{
+    (void)mat;
+    *reinterpret_cast<uint2 *>(wf.rec + WF_REC_QUADS * slot + 5u) = make_uint2(__float_as_uint(t), prim);
+}
+
 #define WF_KEY_DEAD 511u
 #define WF_KEY_BINS 512u
 
@@ -158,9 +168,9 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
             if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; shapes += cnt.shape_tests; }
             if(done)
             {
-                *reinterpret_cast<uint2 *>(wf.rec + WF_REC_QUADS * slot + 5u) = make_uint2(__float_as_uint(t.best_t), t.best_prim);
                 uint32_t mat = 0u;
                 if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
+                wf_store_hit(wf, slot, t.best_t, t.best_prim, mat);
                 uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
                 wf.key[slot] = key;
                 atomicAdd(&sh_hist[key], 1u);
@@ -197,6 +207,184 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
     }
 }
 
+// EXTEND with a warp-wide vote on what to do next.
+//
+// ncu (source page of k_wf_extend, C3 scene): the wide-node visit runs with 27.5 of 32 lanes, but in
+// the primitive loop that follows it the triangle test runs with 1.8 lanes and the box/cylinder test
+// with 9 -- in any one trip only a few rays reach a leaf, and lanes with different kinds of record
+// serialise -- and together they take a third of all issue slots.  Here every trip of the warp does
+// ONE thing: a node visit, one triangle test, or one test of a record of any kind (nodes with a
+// non-triangle record are flagged by the flattener, ORT_NODE_MIXED_KINDS).  A lane that has reached
+// a leaf holds its pending records and takes no further node visit (so its hit bound is as fresh as
+// in k_wf_extend and it visits exactly the same nodes) until the warp votes for its kind of test:
+// when enough lanes wait for it, when it has waited ORT_VOTE_AGE trips, or when no lane has a node
+// to visit.  Results are bit-identical to k_wf_extend.
+#ifndef ORT_VOTE_TRI
+#define ORT_VOTE_TRI 6u
+#endif
+#ifndef ORT_VOTE_MIXED
+#define ORT_VOTE_MIXED 12u
+#endif
+#ifndef ORT_VOTE_AGE
+#define ORT_VOTE_AGE 4u
+#endif
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
+k_wf_extend_v(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned long long *stats, uint32_t *hist)
+{
+    extern __shared__ uint2 smem_stack[];
+    __shared__ uint32_t sh_hist[WF_KEY_BINS];
+    __shared__ uint32_t sh_done;
+    if(threadIdx.x == 0) sh_done = 0u;
+    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh_hist[k] = 0u;
+    __syncthreads();
+    SharedStack st; st.col = smem_stack + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t next = 0u, end = 0u;
+    bool exhausted = false;
+
+    Trav t;
+    t.ng_x = t.ng_y = 0u; t.sp = 0;
+    bool has_ray = false;
+    uint32_t slot = 0u, is_primary = 0u;
+    uint32_t pg_x = 0u, pg_y = 0u, pg_mixed = 0u;          // pending records of the leaf children just reached
+    uint32_t tri_wait = 0u, mixed_wait = 0u;               // warp-uniform: trips the waiting lanes have been held
+    unsigned long long nodes = 0, boxes = 0, shapes = 0, rays = 0;
+
+    for(;;)
+    {
+        uint32_t idle_mask = __ballot_sync(0xFFFFFFFFu, !has_ray);
+        if(!exhausted && (__popc(idle_mask) >= ORT_FETCH_MIN || idle_mask == 0xFFFFFFFFu))
+        {
+            if(next >= end)
+            {
+                uint32_t base = 0u;
+                if(lane == 0) base = atomicAdd(chunk_counter, WF_CHUNK);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                next = base; end = base + WF_CHUNK;
+                if(end > wf.capacity) end = wf.capacity;
+                if(base >= wf.capacity) { exhausted = true; next = end = 0u; }
+            }
+            uint32_t my = next + __popc(idle_mask & ((1u << lane) - 1u));
+            if(!has_ray && my < end)
+            {
+                float4 ro = wf.rec[WF_REC_QUADS * my];
+                if(__float_as_uint(ro.w) == WF_ACTIVE)
+                {
+                    float4 rd = wf.rec[WF_REC_QUADS * my + 1u];
+                    trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
+                    is_primary = __float_as_uint(rd.w);
+                    slot = my;
+                    has_ray = true;
+                    pg_y = 0u;
+                    ++rays;
+                }
+                else { wf.key[my] = WF_KEY_DEAD; atomicAdd(&sh_hist[WF_KEY_DEAD], 1u); }
+            }
+            next += __popc(idle_mask);
+            if(next > end) next = end;
+        }
+        const bool w_visit = has_ray && pg_y == 0u;
+        const bool w_tri = has_ray && pg_y != 0u && pg_mixed == 0u;
+        const bool w_mixed = has_ray && pg_y != 0u && pg_mixed != 0u;
+        const uint32_t n_visit = __popc(__ballot_sync(0xFFFFFFFFu, w_visit));
+        const uint32_t n_tri = __popc(__ballot_sync(0xFFFFFFFFu, w_tri));
+        const uint32_t n_mixed = __popc(__ballot_sync(0xFFFFFFFFu, w_mixed));
+        if((n_visit | n_tri | n_mixed) == 0u)
+        {
+            if(exhausted) break;
+            continue;
+        }
+        uint32_t action;          // 0 visit, 1 triangle test, 2 test of any kind
+        if(n_tri != 0u && (n_tri >= ORT_VOTE_TRI || tri_wait >= ORT_VOTE_AGE)) action = 1u;
+        else if(n_mixed != 0u && (n_mixed >= ORT_VOTE_MIXED || mixed_wait >= ORT_VOTE_AGE)) action = 2u;
+        else if(n_visit != 0u) action = 0u;
+        else action = n_tri >= n_mixed ? 1u : 2u;
+        tri_wait = (action == 1u || n_tri == 0u) ? 0u : tri_wait + 1u;
+        mixed_wait = (action == 2u || n_mixed == 0u) ? 0u : mixed_wait + 1u;
+
+        if(action == 0u)
+        {
+            if(w_visit)
+            {
+                TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
+                uint32_t node_index;
+                trav_visit<COUNT>(scene, t, st, t.best_t, &cnt, &pg_x, &pg_y, &node_index, &pg_mixed);
+                if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; }
+            }
+        }
+        else if(action == 1u)
+        {
+            if(w_tri)
+            {
+                uint32_t prim = pg_x + lsb32(pg_y);
+                pg_y &= pg_y - 1u;
+                const q4 *p = scene.prims + 3u * prim;
+                q4 A = ldq(p), B = ldq(p + 1), C = ldq(p + 2);
+                exact::Hit h = exact::triangle(q3(A), q3(B), q3(C), t.o, t.d);
+                uint32_t rank = f2u(A.w);
+                if(COUNT) ++shapes;
+                if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < t.best_t || (h.t == t.best_t && rank < t.best_rank)))
+                {
+                    t.best_t = h.t; t.best_prim = prim; t.best_rank = rank;
+                }
+            }
+        }
+        else
+        {
+            if(w_mixed)
+            {
+                uint32_t prim = pg_x + lsb32(pg_y), rank, mat;
+                pg_y &= pg_y - 1u;
+                exact::Hit h = intersect_prim(scene, prim, t.o, t.d, t.inv, &rank, &mat);
+                (void)mat;
+                if(COUNT) ++shapes;
+                if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < t.best_t || (h.t == t.best_t && rank < t.best_rank)))
+                {
+                    t.best_t = h.t; t.best_prim = prim; t.best_rank = rank;
+                }
+            }
+        }
+        // a ray with no pending record and no node left in its group pops the stack, or is done
+        if(has_ray && pg_y == 0u && !trav_next(t, st))
+        {
+            uint32_t mat = 0u;
+            if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
+            wf_store_hit(wf, slot, t.best_t, t.best_prim, mat);
+            uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
+            wf.key[slot] = key;
+            atomicAdd(&sh_hist[key], 1u);
+            has_ray = false;
+        }
+    }
+    rays = warp_sum(rays);
+    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); shapes = warp_sum(shapes); }
+    if(lane == 0 && rays)
+    {
+        atomicAdd(&stats[STAT_RAYS], rays);
+        if(COUNT)
+        {
+            atomicAdd(&stats[STAT_NODE_VISITS], nodes);
+            atomicAdd(&stats[STAT_BOX_TESTS], boxes);
+            atomicAdd(&stats[STAT_SHAPE_TESTS], shapes);
+        }
+    }
+    __syncwarp();
+    uint32_t finished = 0u;
+    if(lane == 0) { __threadfence_block(); finished = atomicAdd(&sh_done, 1u); }
+    finished = __shfl_sync(0xFFFFFFFFu, finished, 0);
+    if(finished == 3u)
+    {
+        __threadfence_block();
+        for(uint32_t k = lane; k < WF_KEY_BINS; k += 32u)
+        {
+            uint32_t v = ((volatile uint32_t *)sh_hist)[k];
+            if(v) atomicAdd(&hist[k], v);
+        }
+    }
+}
+
 // EXTEND with primitive-test redistribution.
 //
 // ncu (source page of the kernel above, C3 scene): the wide-node visit runs with 28.8 of 32 lanes,
@@ -211,6 +399,9 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
 // wins".  Culling reads the same word, so it only ever uses a bound that is already proven.
 // Slot ranges are handed out in chunks from a global counter, so warps finish together.
 #define WF_QCAP 128u
+#ifndef ORT_Q_BUSY
+#define ORT_Q_BUSY 16u       // partial batches wait while at least this many lanes still have node work (33 = never wait)
+#endif
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
@@ -348,7 +539,7 @@ k_wf_extend_q(SceneView scene, WfBuffers wf, const uint32_t *__restrict__ rank_t
             {
                 uint32_t count = q_tail[q] - q_head[q];
                 if(count == 0u) break;
-                if(count < 32u && busy >= 16u) break;
+                if(count < 32u && busy >= ORT_Q_BUSY) break;
                 uint32_t n = count < 32u ? count : 32u;
                 uint32_t e = queue[q][(q_head[q] + lane) % WF_QCAP];
                 uint32_t owner = (e >> 27), prim = e & 0x07FFFFFFu;
@@ -378,7 +569,7 @@ k_wf_extend_q(SceneView scene, WfBuffers wf, const uint32_t *__restrict__ rank_t
                 prim = rank_to_prim[rank];
                 mat = f2u(ldq(scene.prims + 3u * prim + 1u).w);
             }
-            *reinterpret_cast<uint2 *>(wf.rec + WF_REC_QUADS * slot + 5u) = make_uint2((uint32_t)(best >> 32), prim);
+            wf_store_hit(wf, slot, __uint_as_float((uint32_t)(best >> 32)), prim, mat);
             uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
             wf.key[slot] = key;
             atomicAdd(&sh_hist[key], 1u);

@@ -145,3 +145,15 @@ def test_counters_report_less_work_than_the_reference(gpu_testscene, testscene_h
     n = len(o)
     assert 0 < c["shape_tests"] / n < 0.2 * ref["shape_tests"] / n
     assert 0 < c["node_visits"] / n < ref["node_visits"] / n
+
+
+def test_shared_reciprocal_division_is_ieee(ort):
+    """normalize() on the device forms a/|a| from one reciprocal (csrc/core_math.h, div3_shared);
+    every quotient must have the bits of the plain IEEE-754 division -- zeros, subnormals, infinities,
+    NaNs and operands on both sides of the fast path's range guard included"""
+    total = 0
+    for seed in (1, 2, 3, 4):
+        tested, bad = ort.selftest_div3(1 << 30, seed)
+        assert bad == 0, (seed, bad, tested)
+        total += tested
+    assert total >= 1 << 32
