@@ -10,7 +10,7 @@
 //                 stream (ray.cpp:1215-1246) -- or pull the next (pixel, chunk) stream from the
 //                 global work counter.  A slot therefore always leaves this kernel holding a
 //                 ray (path regeneration), so the wavefront stays full until the work runs out
-//                 and no compaction pass is needed while it does.
+//                 and no pool-wide compaction pass is needed while it does.
 //   k_wf_extend   per slot: closest hit of its ray (bvh.h) -> (t, primitive)
 //
 // Why split: the single-kernel form is ~6000 SASS instructions (96 KB); ncu shows its
@@ -683,9 +683,27 @@ __device__ __forceinline__ void wf_finish_hit(const SceneView &s, uint32_t prim,
 
 // `sorted`: thread j handles slot perm[j] for j < *live (slots grouped by material, so the lanes
 // of a warp mostly take the same branches of the BSDF code); else thread j handles slot j.
+//
+// Two phases per block.  Phase 1, every thread: shade its slot's hit and sample the next bounce.
+// Phase 2: the slots whose path ended -- roulette, a light, a miss: about one in five, scattered
+// over the warps -- are compacted through shared memory and the first threads of the block, with
+// full warps, ACCUMULATE the finished stream, pull the next one and GENERATE the camera ray.  (ncu:
+// done in place by the thread that owned the slot, these ~300 instructions ran with 6.8 of 32 lanes
+// and every warp paid for them.)
+struct WfRegen           // what phase 2 needs to know about a slot, 32 B
+{
+    float cx, cy, cz;            // radiance sum of the stream so far
+    uint32_t series, pixel_index, samples_left, chunk, slot;
+};
+
 __global__ void __launch_bounds__(128, ORT_SHADE_MIN_BLOCKS)
 k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uint32_t *live, int sorted)
 {
+    __shared__ WfRegen sh_regen[128];
+    __shared__ uint32_t sh_count;
+    if(threadIdx.x == 0) sh_count = 0u;
+    __syncthreads();
+
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n_samples = 0;
     unsigned int still_active = 0;
@@ -696,115 +714,140 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
         in_range = j < *live;
         if(in_range) i = wf.perm[j];
     }
+    // ---- phase 1: shade + next bounce ----
+    bool regen = false;
+    WfRegen rg;
+    rg.cx = rg.cy = rg.cz = 0.f; rg.series = 0u; rg.pixel_index = 0xFFFFFFFFu; rg.samples_left = 0u; rg.chunk = 0u; rg.slot = i;
     if(in_range)
     {
         float4 *rec = wf.rec + (size_t)WF_REC_QUADS * i;
         float4 ro = rec[0];
         uint32_t state = __float_as_uint(ro.w);
-        if(state != WF_DEAD)
+        if(state == WF_ACTIVE)
         {
             Path p;
-            f3 color = mk3(0.f, 0.f, 0.f);
-            uint32_t samples_left = 0, pixel_index = 0xFFFFFFFFu, chunk = 0;
-            bool have_ray = false;
-            if(state == WF_ACTIVE)
-            {
-                float4 rd = rec[1], swo = rec[2], sw = rec[3], scol = rec[4], hq = rec[5];
-                uint2 h = make_uint2(__float_as_uint(hq.x), __float_as_uint(hq.y));
-                chunk = __float_as_uint(hq.z);
-                p.origin = mk3(ro.x, ro.y, ro.z); p.dir = mk3(rd.x, rd.y, rd.z);
-                p.wo = mk3(swo.x, swo.y, swo.z); p.series = __float_as_uint(swo.w);
-                p.weight = mk3(sw.x, sw.y, sw.z); pixel_index = __float_as_uint(sw.w);
-                color = mk3(scol.x, scol.y, scol.z);
-                uint32_t sl = __float_as_uint(scol.w);
-                const bool primary = (sl >> 31) != 0u;
-                samples_left = sl & 0x7FFFFFFFu;
-                p.normal = mk3(0.f, 0.f, 0.f); p.mat = 0u;
-                uint32_t mat; f3 nrm;
-                wf_finish_hit(a.scene, h.y, p.origin, p.dir, &mat, &nrm);
-                float hit_t = __uint_as_float(h.x);
-                bool alive = primary ? shade_primary(a.pc, &p, hit_t, mat, nrm, &color)
-                                     : shade_bounce(a.pc, &p, hit_t, mat, nrm, &color);
-                have_ray = alive && next_bounce(a.pc, &p);
-            }
-            bool primary_next = false;
-            if(!have_ray)
-            {
-                bool dead = false;
-                if(samples_left == 0)
-                {
-                    // ---- accumulate the finished stream (ray.cpp:1428) ----
-                    if(pixel_index != 0xFFFFFFFFu)
-                    {
-                        if(a.accum)
-                        {
-                            unsigned long long *dst = (unsigned long long *)(a.accum + 4ull * pixel_index);
-                            atomicAdd(dst + 0, (unsigned long long)to_fixed(color.x));
-                            atomicAdd(dst + 1, (unsigned long long)to_fixed(color.y));
-                            atomicAdd(dst + 2, (unsigned long long)to_fixed(color.z));
-                        }
-                        else
-                        {
-                            f3 px = color / (float)a.spp;
-                            a.rgb[3ull * pixel_index + 0] = px.x;
-                            a.rgb[3ull * pixel_index + 1] = px.y;
-                            a.rgb[3ull * pixel_index + 2] = px.z;
-                        }
-                    }
-                    // ---- next stream from the global work counter ----
-                    int x = -1, y = -1;
-                    for(;;)
-                    {
-                        unsigned long long item = atomicAdd(a.work_counter, 1ull);
-                        if(item >= a.total_items) break;
-                        uint32_t lane = (uint32_t)(item & 31ull);
-                        unsigned long long blk = item >> 5;
-                        uint32_t bx = (uint32_t)(blk % a.blocks_x); blk /= a.blocks_x;
-                        uint32_t by = (uint32_t)(blk % a.blocks_y); blk /= a.blocks_y;
-                        int lx = (int)(bx * 8u + (lane & 7u)), ly = (int)(by * 4u + (lane >> 3));
-                        if(lx < a.tile_w && ly < a.tile_h)
-                        {
-                            x = a.tile_min_x + lx; y = a.tile_min_y + ly;
-                            chunk = a.chunk_begin + (uint32_t)blk;
-                            break;
-                        }
-                    }
-                    if(x < 0) dead = true;
-                    else
-                    {
-                        pixel_index = (uint32_t)(y * a.pc.width + x);
-                        samples_left = a.chunk_spp;
-                        if((chunk + 1u) * a.chunk_spp > a.spp) samples_left = a.spp - chunk * a.chunk_spp;
-                        p.series = ort_stream_seed(a.base_seed, pixel_index, chunk);
-                        color = mk3(0.f, 0.f, 0.f);
-                    }
-                }
-                if(dead)
-                {
-                    rec[0] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_DEAD));
-                }
-                else
-                {
-                    // ---- generate (ray.cpp:1215-1246) ----
-                    int x = (int)(pixel_index % (uint32_t)a.pc.width), y = (int)(pixel_index / (uint32_t)a.pc.width);
-                    generate_primary(a.pc, pixel_focal_point(a.pc, x, y), &p);
-                    --samples_left;
-                    n_samples = 1;
-                    primary_next = true;
-                    have_ray = true;
-                }
-            }
-            if(have_ray)
+            float4 rd = rec[1], swo = rec[2], sw = rec[3], scol = rec[4], hq = rec[5];
+            uint2 h = make_uint2(__float_as_uint(hq.x), __float_as_uint(hq.y));
+            const uint32_t chunk = __float_as_uint(hq.z);
+            p.origin = mk3(ro.x, ro.y, ro.z); p.dir = mk3(rd.x, rd.y, rd.z);
+            p.wo = mk3(swo.x, swo.y, swo.z); p.series = __float_as_uint(swo.w);
+            p.weight = mk3(sw.x, sw.y, sw.z);
+            const uint32_t pixel_index = __float_as_uint(sw.w);
+            f3 color = mk3(scol.x, scol.y, scol.z);
+            uint32_t sl = __float_as_uint(scol.w);
+            const bool primary = (sl >> 31) != 0u;
+            const uint32_t samples_left = sl & 0x7FFFFFFFu;
+            p.normal = mk3(0.f, 0.f, 0.f); p.mat = 0u;
+            uint32_t mat; f3 nrm;
+            wf_finish_hit(a.scene, h.y, p.origin, p.dir, &mat, &nrm);
+            float hit_t = __uint_as_float(h.x);
+            bool alive = primary ? shade_primary(a.pc, &p, hit_t, mat, nrm, &color)
+                                 : shade_bounce(a.pc, &p, hit_t, mat, nrm, &color);
+            if(alive && next_bounce(a.pc, &p))
             {
                 rec[0] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
-                rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(primary_next ? 1u : 0u));
+                rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(0u));
                 rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
                 rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
-                rec[4] = make_float4(color.x, color.y, color.z,
-                                     __uint_as_float(samples_left | (primary_next ? 0x80000000u : 0u)));
+                rec[4] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left));
                 rec[5] = make_float4(0.f, 0.f, __uint_as_float(chunk), 0.f);
                 still_active = 1;
             }
+            else
+            {
+                regen = true;
+                rg.cx = color.x; rg.cy = color.y; rg.cz = color.z;
+                rg.series = p.series; rg.pixel_index = pixel_index; rg.samples_left = samples_left; rg.chunk = chunk;
+            }
+        }
+        else if(state == WF_FRESH) regen = true;      // no stream yet: samples_left 0, no pixel
+    }
+    // ---- compaction of the slots to regenerate ----
+    {
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, regen);
+        uint32_t base = 0u;
+        if(lane == 0 && m) base = atomicAdd(&sh_count, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if(regen) sh_regen[base + __popc(m & ((1u << lane) - 1u))] = rg;
+    }
+    __syncthreads();
+    // ---- phase 2: accumulate / next stream / generate, with full warps ----
+    if(threadIdx.x < sh_count)
+    {
+        rg = sh_regen[threadIdx.x];
+        float4 *rec = wf.rec + (size_t)WF_REC_QUADS * rg.slot;
+        f3 color = mk3(rg.cx, rg.cy, rg.cz);
+        uint32_t samples_left = rg.samples_left, pixel_index = rg.pixel_index, chunk = rg.chunk;
+        Path p;
+        p.series = rg.series;
+        bool dead = false;
+        if(samples_left == 0)
+        {
+            // ---- accumulate the finished stream (ray.cpp:1428) ----
+            if(pixel_index != 0xFFFFFFFFu)
+            {
+                if(a.accum)
+                {
+                    unsigned long long *dst = (unsigned long long *)(a.accum + 4ull * pixel_index);
+                    atomicAdd(dst + 0, (unsigned long long)to_fixed(color.x));
+                    atomicAdd(dst + 1, (unsigned long long)to_fixed(color.y));
+                    atomicAdd(dst + 2, (unsigned long long)to_fixed(color.z));
+                }
+                else
+                {
+                    f3 px = color / (float)a.spp;
+                    a.rgb[3ull * pixel_index + 0] = px.x;
+                    a.rgb[3ull * pixel_index + 1] = px.y;
+                    a.rgb[3ull * pixel_index + 2] = px.z;
+                }
+            }
+            // ---- next stream from the global work counter ----
+            int x = -1, y = -1;
+            for(;;)
+            {
+                unsigned long long item = atomicAdd(a.work_counter, 1ull);
+                if(item >= a.total_items) break;
+                uint32_t lane = (uint32_t)(item & 31ull);
+                unsigned long long blk = item >> 5;
+                uint32_t bx = (uint32_t)(blk % a.blocks_x); blk /= a.blocks_x;
+                uint32_t by = (uint32_t)(blk % a.blocks_y); blk /= a.blocks_y;
+                int lx = (int)(bx * 8u + (lane & 7u)), ly = (int)(by * 4u + (lane >> 3));
+                if(lx < a.tile_w && ly < a.tile_h)
+                {
+                    x = a.tile_min_x + lx; y = a.tile_min_y + ly;
+                    chunk = a.chunk_begin + (uint32_t)blk;
+                    break;
+                }
+            }
+            if(x < 0) dead = true;
+            else
+            {
+                pixel_index = (uint32_t)(y * a.pc.width + x);
+                samples_left = a.chunk_spp;
+                if((chunk + 1u) * a.chunk_spp > a.spp) samples_left = a.spp - chunk * a.chunk_spp;
+                p.series = ort_stream_seed(a.base_seed, pixel_index, chunk);
+                color = mk3(0.f, 0.f, 0.f);
+            }
+        }
+        if(dead)
+        {
+            rec[0] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_DEAD));
+        }
+        else
+        {
+            // ---- generate (ray.cpp:1215-1246) ----
+            int x = (int)(pixel_index % (uint32_t)a.pc.width), y = (int)(pixel_index / (uint32_t)a.pc.width);
+            generate_primary(a.pc, pixel_focal_point(a.pc, x, y), &p);
+            --samples_left;
+            n_samples = 1;
+            rec[0] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
+            rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(1u));
+            rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
+            rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
+            rec[4] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left | 0x80000000u));
+            rec[5] = make_float4(0.f, 0.f, __uint_as_float(chunk), 0.f);
+            still_active += 1;
         }
     }
     n_samples = warp_sum(n_samples);
