@@ -249,6 +249,27 @@ void ort_free(void *p);
 int ort_write_hdr(const char *path, const ort_v3 *pixels, int32_t width, int32_t height);
 uint32_t ort_v3_to_rgbe(ort_v3 color);
 
+/* The same encoding on the device.  RGBE words come out in FILE order -- output
+ * row r is buffer row height-1-r, as the reference's writer walks the buffer (macos_main.mm:686-705)
+ * -- so the file is the header followed by the words as they are:
+ *   ort_rgbe_encode_device         float3 pixels on the device -> uint32 RGBE[height*width]
+ *   ort_accum_resolve_rgbe_device  the int64 fixed-point sums (e.g. straight out of the NCCL reduce)
+ *                                  -> RGBE, resolve (ray.cpp:1428) and encode fused in one pass
+ *   ort_render_rgbe                ort_render for a whole image, returning RGBE words: 4 bytes per
+ *                                  pixel cross PCIe instead of 12
+ *   ort_render_hdr                 the same, written to `path`: byte-identical to ort_render
+ *                                  followed by ort_write_hdr
+ *   ort_write_hdr_rgbe             header + words (host) */
+int ort_rgbe_encode_device(OrtScene *scene, const void *rgb_device, int32_t width, int32_t height,
+                           void *rgbe_device, void *stream);
+int ort_accum_resolve_rgbe_device(OrtScene *scene, const void *accum_device, int32_t width, int32_t height,
+                                  uint32_t ray_per_pixel_count, void *rgbe_device, void *stream);
+int ort_render_rgbe(OrtScene *scene, const OrtCamera *camera, const OrtRenderParams *params,
+                    uint32_t *rgbe_out, OrtRenderStats *stats);
+int ort_render_hdr(OrtScene *scene, const OrtCamera *camera, const OrtRenderParams *params,
+                   const char *path, OrtRenderStats *stats);
+int ort_write_hdr_rgbe(const char *path, const uint32_t *rgbe_words, int32_t width, int32_t height);
+
 /* ------------------------------------------------------------------------
  * Seed of the sample stream of (pixel, chunk).  Part of the boundary's
  * contract: the CPU oracle uses the same function.  Never returns 0 (0 is the

@@ -104,6 +104,11 @@ def lib(path=None):
     L.ort_render_accumulate_device.argtypes = [vp, vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
     L.ort_accum_zero_device.argtypes = [vp, vp, c_i32, c_i32, vp]
     L.ort_accum_resolve_device.argtypes = [vp, vp, c_i32, c_i32, c_u32, vp, vp]
+    L.ort_rgbe_encode_device.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
+    L.ort_accum_resolve_rgbe_device.argtypes = [vp, vp, c_i32, c_i32, c_u32, vp, vp]
+    L.ort_render_rgbe.argtypes = [vp, vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
+    L.ort_render_hdr.argtypes = [vp, vp, C.POINTER(RenderParams), C.c_char_p, C.POINTER(RenderStats)]
+    L.ort_write_hdr_rgbe.argtypes = [C.c_char_p, vp, c_i32, c_i32]
     L.ort_raycast_batch.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp, C.POINTER(RenderStats)]
     L.ort_raycast_batch_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp, vp]
     L.ort_raycast_brute_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp]
@@ -246,6 +251,28 @@ class Scene:
         st = RenderStats()
         _check(self.L.ort_render(self.h, _as_ptr(camera_ptr), C.byref(params), _ptr(out), C.byref(st)), self.L)
         return out, st.as_dict()
+
+    def render_rgbe(self, camera_ptr, params):
+        """ort_render_rgbe: (uint32[H,W] RGBE words in .hdr file order -- row 0 = top --, stats dict)"""
+        W, H = params.output_width, params.output_height
+        out = np.zeros((H, W), np.uint32)
+        st = RenderStats()
+        _check(self.L.ort_render_rgbe(self.h, _as_ptr(camera_ptr), C.byref(params), _ptr(out), C.byref(st)), self.L)
+        return out, st.as_dict()
+
+    def render_hdr(self, camera_ptr, params, path):
+        """ort_render_hdr: renders and writes the Radiance .hdr file; returns the stats dict"""
+        st = RenderStats()
+        _check(self.L.ort_render_hdr(self.h, _as_ptr(camera_ptr), C.byref(params), str(path).encode(), C.byref(st)), self.L)
+        return st.as_dict()
+
+    def rgbe_encode_device(self, rgb_ptr, width, height, rgbe_ptr, stream=None):
+        _check(self.L.ort_rgbe_encode_device(self.h, vp(rgb_ptr), width, height, vp(rgbe_ptr),
+                                             vp(stream) if stream else None), self.L)
+
+    def accum_resolve_rgbe_device(self, accum_ptr, width, height, spp, rgbe_ptr, stream=None):
+        _check(self.L.ort_accum_resolve_rgbe_device(self.h, vp(accum_ptr), width, height, spp, vp(rgbe_ptr),
+                                                    vp(stream) if stream else None), self.L)
 
     def tiled_raytrace_bvh(self, camera_ptr, output_buffer, output_width, output_height,
                            tile_min_x, tile_min_y, tile_one_past_max_x, tile_one_past_max_y,

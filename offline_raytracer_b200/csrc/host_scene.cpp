@@ -436,6 +436,22 @@ int write_hdr(const char *path, const ort_v3 *pixels, int32_t width, int32_t hei
     return ORT_OK;
 }
 
+// the same file from RGBE words already in file order (encoded on the device, kernels.cuh)
+int write_hdr_rgbe(const char *path, const uint32_t *words, int32_t width, int32_t height, std::string *err)
+{
+    if(width <= 0 || height <= 0 || !words) { *err = "bad image"; return ORT_ERR_ARG; }
+    FILE *f = fopen(path, "wb");
+    if(!f) { *err = std::string("cannot create ") + path; return ORT_ERR_IO; }
+    fprintf(f, "#?RADIANCE\n");
+    fprintf(f, "FORMAT=32-bit_rle_rgbe\n\n");
+    fprintf(f, "+Y %d +X %d\n", height, width);
+    size_t n = (size_t)width * height;
+    bool ok = fwrite(words, 4, n, f) == n;
+    fclose(f);
+    if(!ok) { *err = "short write"; return ORT_ERR_IO; }
+    return ORT_OK;
+}
+
 } // namespace ort
 
 // ---------------------------------------------------------------------------
@@ -495,6 +511,14 @@ int ort_write_hdr(const char *path, const ort_v3 *pixels, int32_t width, int32_t
 {
     std::string err;
     int rc = ort::write_hdr(path, pixels, width, height, &err);
+    if(rc != ORT_OK) ort_set_last_error_(err.c_str());
+    return rc;
+}
+
+int ort_write_hdr_rgbe(const char *path, const uint32_t *rgbe_words, int32_t width, int32_t height)
+{
+    std::string err;
+    int rc = ort::write_hdr_rgbe(path, rgbe_words, width, height, &err);
     if(rc != ORT_OK) ort_set_last_error_(err.c_str());
     return rc;
 }

@@ -72,4 +72,5 @@ int assemble_scene(const char *scn_path, const char *base_dir, int32_t width, in
                    OrtHostScene *hs, std::string *err);
 uint32_t v3_to_rgbe(ort_v3 color);
 int write_hdr(const char *path, const ort_v3 *pixels, int32_t width, int32_t height, std::string *err);
+int write_hdr_rgbe(const char *path, const uint32_t *words, int32_t width, int32_t height, std::string *err);
 }

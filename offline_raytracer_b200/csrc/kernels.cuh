@@ -254,6 +254,45 @@ __global__ void k_resolve_fixed(const long long *__restrict__ accum, float *__re
         rgb[3 * pix + k] = (float)((double)accum[4 * pix + k] * inv) / (float)spp;
 }
 
+// Radiance RGBE pixel, v3_to_rgbe (macos_main.mm:242-261) with the same float operations as the
+// host form (host_scene.cpp): frexpf is exact, the product and the quotient are IEEE (no
+// contraction), roundf rounds halves away from zero on both sides.  Defined for the non-negative
+// radiance the integrator produces (a negative component converts to 0 here).
+__device__ __forceinline__ uint32_t rgbe_encode(float x, float y, float z)
+{
+    float m = ref_max(ref_max(x, y), z);
+    if(!(m >= 1e-32f)) return 0u;
+    int e;
+    float denom = frexpf(m, &e) * 255.0f / m;
+    return ((uint32_t)roundf(x * denom) << 0) | ((uint32_t)roundf(y * denom) << 8) |
+           ((uint32_t)roundf(z * denom) << 16) | ((uint32_t)(e + 128) << 24);
+}
+
+// float3 pixels (buffer row 0 = bottom) -> RGBE words in FILE order: the writer emits buffer rows
+// h-1 -> 0 (macos_main.mm:686-705), so output row r is buffer row h-1-r
+__global__ void k_rgbe_from_rgb(const float *__restrict__ rgb, uint32_t *__restrict__ rgbe, int32_t w, int32_t h)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= w * h) return;
+    int x = i % w, r = i / w;
+    size_t pix = (size_t)(h - 1 - r) * w + x;
+    rgbe[i] = rgbe_encode(rgb[3 * pix], rgb[3 * pix + 1], rgb[3 * pix + 2]);
+}
+
+// the same fused after the fixed-point resolve (ray.cpp:1428 + macos_main.mm:682-707): one pass
+// from the int64 sums -- e.g. straight out of the NCCL reduce -- to the bytes of the .hdr file
+__global__ void k_rgbe_from_fixed(const long long *__restrict__ accum, uint32_t *__restrict__ rgbe, int32_t w, int32_t h, uint32_t spp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= w * h) return;
+    int x = i % w, r = i / w;
+    size_t pix = (size_t)(h - 1 - r) * w + x;
+    const double inv = 1.0 / (double)(1 << ORT_ACCUM_FRAC_BITS);
+    float c[3];
+    for(int k = 0; k < 3; ++k) c[k] = (float)((double)accum[4 * pix + k] * inv) / (float)spp;
+    rgbe[i] = rgbe_encode(c[0], c[1], c[2]);
+}
+
 // FP32-pipe roofline denominator (MEASURED_PEAKS.json has no FP32 figure).
 // Eight independent multiply-add chains per thread; with -fmad=false each `a*b+c` is
 // an FMUL and an FADD, i.e. the same non-FMA instruction mix the intersectors issue.

@@ -63,6 +63,7 @@ struct OrtScene
     unsigned long long *d_stats;        // STAT_COUNT counters
     long long *d_accum; size_t accum_pixels;
     float *d_rgb; size_t rgb_pixels;
+    uint32_t *d_rgbe = 0; size_t rgbe_capacity = 0;      // RGBE words in file order (ort_render_rgbe)
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     int sm_count;
@@ -561,7 +562,7 @@ int ort_scene_destroy(OrtScene *s)
     if(s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_rank_to_prim);
     cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_cyl); cudaFree(s->d_materials);
-    cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb);
+    cudaFree(s->d_light_is_sphere); cudaFree(s->d_stats); cudaFree(s->d_accum); cudaFree(s->d_rgb); cudaFree(s->d_rgbe);
     cudaFree(s->wf.rec); cudaFree(s->d_active);
     if(s->wf_ready)
     {
@@ -608,20 +609,17 @@ void ort_render_params_default(OrtRenderParams *p, int32_t width, int32_t height
     p->focus_target[0] = 0.0f; p->focus_target[1] = 0.0f; p->focus_target[2] = 0.2f;   // ray.cpp:1198
 }
 
-int ort_render(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, ort_v3 *output_buffer, OrtRenderStats *stats)
+// the device part of ort_render: leaves the image as float3 pixels in s->d_rgb (and, when the
+// job has more than one chunk, the fixed-point sums in s->d_accum); *fixed_out tells which
+static int render_to_device(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, bool *fixed_out, uint32_t *launches)
 {
-    if(!s || !camera || !output_buffer) return fail(ORT_ERR_ARG, "null argument");
-    int rc = check_params(P);
-    if(rc != ORT_OK) return rc;
-    CUDA_TRY(cudaSetDevice(s->device));
     ChunkPlan cp = plan_chunks(P);
     size_t pixels = (size_t)P->output_width * P->output_height;
     int tw = P->tile_one_past_max_x - P->tile_min_x, th = P->tile_one_past_max_y - P->tile_min_y;
-    rc = ensure_rgb(s, pixels);
+    int rc = ensure_rgb(s, pixels);
     if(rc != ORT_OK) return rc;
     const bool fixed = cp.n_chunks > 1;
     if(fixed) { rc = ensure_accum(s, pixels); if(rc != ORT_OK) return rc; }
-    uint32_t launches = 0;
     cudaStream_t st = s->stream;
     CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(s->ev0, st));
@@ -632,7 +630,7 @@ int ort_render(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, o
         size_t cnt = (size_t)th * P->output_width * 4;
         if(cnt) CUDA_TRY(cudaMemsetAsync(s->d_accum + off, 0, cnt * sizeof(long long), st));
     }
-    rc = launch_render(s, camera, P, cp, fixed ? s->d_accum : 0, fixed ? 0 : s->d_rgb, st, &launches);
+    rc = launch_render(s, camera, P, cp, fixed ? s->d_accum : 0, fixed ? 0 : s->d_rgb, st, launches);
     if(rc != ORT_OK) return rc;
     if(fixed && tw > 0 && th > 0)
     {
@@ -640,8 +638,24 @@ int ort_render(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, o
         k_resolve_fixed<<<(n + 255) / 256, 256, 0, st>>>(s->d_accum, s->d_rgb, P->output_width, P->tile_min_x, P->tile_min_y,
                                                           tw, th, P->ray_per_pixel_count);
         CUDA_TRY(cudaGetLastError());
-        launches++;
+        (*launches)++;
     }
+    *fixed_out = fixed;
+    return ORT_OK;
+}
+
+int ort_render(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, ort_v3 *output_buffer, OrtRenderStats *stats)
+{
+    if(!s || !camera || !output_buffer) return fail(ORT_ERR_ARG, "null argument");
+    int rc = check_params(P);
+    if(rc != ORT_OK) return rc;
+    CUDA_TRY(cudaSetDevice(s->device));
+    int tw = P->tile_one_past_max_x - P->tile_min_x, th = P->tile_one_past_max_y - P->tile_min_y;
+    uint32_t launches = 0;
+    bool fixed = false;
+    cudaStream_t st = s->stream;
+    rc = render_to_device(s, camera, P, &fixed, &launches);
+    if(rc != ORT_OK) return rc;
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     if(tw > 0 && th > 0)
     {
@@ -656,6 +670,74 @@ int ort_render(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, o
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     return read_stats(s, st, stats, ms, launches);
+}
+
+int ort_rgbe_encode_device(OrtScene *s, const void *rgb_device, int32_t width, int32_t height, void *rgbe_device, void *stream)
+{
+    if(!s || !rgb_device || !rgbe_device || width <= 0 || height <= 0) return fail(ORT_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int n = width * height;
+    k_rgbe_from_rgb<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float *)rgb_device, (uint32_t *)rgbe_device, width, height);
+    CUDA_TRY(cudaGetLastError());
+    return ORT_OK;
+}
+
+int ort_accum_resolve_rgbe_device(OrtScene *s, const void *accum_device, int32_t width, int32_t height,
+                                  uint32_t ray_per_pixel_count, void *rgbe_device, void *stream)
+{
+    if(!s || !accum_device || !rgbe_device || width <= 0 || height <= 0 || ray_per_pixel_count == 0)
+        return fail(ORT_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int n = width * height;
+    k_rgbe_from_fixed<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const long long *)accum_device, (uint32_t *)rgbe_device,
+                                                                        width, height, ray_per_pixel_count);
+    CUDA_TRY(cudaGetLastError());
+    return ORT_OK;
+}
+
+int ort_render_rgbe(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, uint32_t *rgbe_out, OrtRenderStats *stats)
+{
+    if(!s || !camera || !rgbe_out) return fail(ORT_ERR_ARG, "null argument");
+    int rc = check_params(P);
+    if(rc != ORT_OK) return rc;
+    if(P->tile_min_x != 0 || P->tile_min_y != 0 || P->tile_one_past_max_x != P->output_width || P->tile_one_past_max_y != P->output_height)
+        return fail(ORT_ERR_ARG, "ort_render_rgbe renders whole images: the tile must cover the output");
+    CUDA_TRY(cudaSetDevice(s->device));
+    size_t pixels = (size_t)P->output_width * P->output_height;
+    if(s->rgbe_capacity < pixels)
+    {
+        cudaFree(s->d_rgbe); s->d_rgbe = 0; s->rgbe_capacity = 0;
+        CUDA_TRY(cudaMalloc((void **)&s->d_rgbe, pixels * sizeof(uint32_t)));
+        s->rgbe_capacity = pixels;
+    }
+    uint32_t launches = 0;
+    bool fixed = false;
+    cudaStream_t st = s->stream;
+    rc = render_to_device(s, camera, P, &fixed, &launches);
+    if(rc != ORT_OK) return rc;
+    if(fixed)
+        k_rgbe_from_fixed<<<(unsigned)((pixels + 255) / 256), 256, 0, st>>>(s->d_accum, s->d_rgbe, P->output_width, P->output_height,
+                                                                              P->ray_per_pixel_count);
+    else
+        k_rgbe_from_rgb<<<(unsigned)((pixels + 255) / 256), 256, 0, st>>>(s->d_rgb, s->d_rgbe, P->output_width, P->output_height);
+    CUDA_TRY(cudaGetLastError());
+    launches++;
+    CUDA_TRY(cudaEventRecord(s->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(rgbe_out, s->d_rgbe, pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    return read_stats(s, st, stats, ms, launches);
+}
+
+int ort_render_hdr(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, const char *path, OrtRenderStats *stats)
+{
+    if(!path || !P) return fail(ORT_ERR_ARG, "null argument");
+    if(P->output_width <= 0 || P->output_height <= 0) return fail(ORT_ERR_ARG, "bad image size");
+    std::vector<uint32_t> words((size_t)P->output_width * P->output_height);
+    int rc = ort_render_rgbe(s, camera, P, words.data(), stats);
+    if(rc != ORT_OK) return rc;
+    return ort_write_hdr_rgbe(path, words.data(), P->output_width, P->output_height);
 }
 
 int ort_tiled_raytrace_bvh(OrtScene *scene, const OrtCamera *camera, ort_v3 *output_buffer,

@@ -212,3 +212,34 @@ def test_wavefront_small_pool_and_unsorted_give_the_same_image(ort, testscene_ho
         img, _ = sc.render(testscene_host.camera, P)
         assert np.array_equal(bits(base), bits(img)), variant
     sc.close()
+
+
+def test_hdr_written_from_the_device_is_byte_identical(ort, testscene_host, tmp_path):
+    """RGBE encoded on the device (fused after the fixed-point resolve) gives the very
+    file that ort_render + the host writer (v3_to_rgbe, macos_main.mm:242-287, 682-707) give"""
+    import torch
+    sc = ort.Scene(testscene_host.world, testscene_host.root, 0)
+    for spp, chunk in ((4, 2), (3, 0)):          # several chunks (fixed-point path) / one chunk (float path)
+        P = ort.default_params(W, H, spp, chunk_spp=chunk, kernel=ort.ORT_KERNEL_WAVEFRONT)
+        img, _ = sc.render(testscene_host.camera, P)
+        a, b = tmp_path / "host.hdr", tmp_path / "device.hdr"
+        ort.write_hdr(str(a), img)
+        st = sc.render_hdr(testscene_host.camera, P, b)
+        assert st["samples"] == W * H * spp
+        assert a.read_bytes() == b.read_bytes()
+        words, _ = sc.render_rgbe(testscene_host.camera, P)
+        want = np.array([[ort.v3_to_rgbe(img[H - 1 - r, x]) for x in range(W)] for r in range(0, H, 17)], np.uint32)
+        assert np.array_equal(words[::17], want)
+    # the stand-alone encoder on arbitrary device pixels: zeros, tiny, huge, mixed magnitudes
+    rng = np.random.default_rng(5)
+    px = (rng.random((64, 96, 3), np.float32) * np.float32(10.0) ** rng.integers(-36, 30, (64, 96, 1)).astype(np.float32)).astype(np.float32)
+    px[0, :8] = 0.0
+    px[1, :8] = np.float32(1e-33)
+    d_px = torch.from_numpy(px).cuda()
+    d_out = torch.zeros((64, 96), dtype=torch.int32, device="cuda")
+    sc.rgbe_encode_device(d_px.data_ptr(), 96, 64, d_out.data_ptr())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint32)
+    want = np.array([[ort.v3_to_rgbe(px[63 - r, x]) for x in range(96)] for r in range(64)], np.uint32)
+    assert np.array_equal(got, want)
+    sc.close()
