@@ -85,6 +85,32 @@ typedef struct OrtSceneInfo
 
 int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node,
                      int device, OrtScene **scene_out);
+
+/* The same, choosing where the acceleration structure is built.
+ * ORT_BUILD_ON_DEVICE: Morton sort, PLOC clustering and the collapse to the 8-wide layout run as
+ * CUDA kernels (csrc/bvh_build.h/.cuh) instead of the host's binned-SAH builder -- the replacement
+ * for the minutes the reference spends in push_shape_inside_node / validate_nodes_and_reallocate_shapes
+ * (code/ray.cpp:1799-2045) on large scenes.  Hits are bit-identical either way: the structure only
+ * decides which records are tested.  ort_scene_create honours ORT_BVH_BUILD=device in the environment. */
+#define ORT_BUILD_ON_DEVICE 1u
+int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node,
+                        int device, uint32_t flags, OrtScene **scene_out);
+
+typedef struct OrtBuildStats
+{
+    uint32_t on_device;          /* 1 = built by the CUDA kernels */
+    uint32_t ploc_iterations;    /* clustering rounds (device build) */
+    uint32_t wide_depth;         /* levels of the 8-wide tree */
+    float    collect_s;          /* host: decoding the octree's push buffers into ranked records */
+    float    prepare_s;          /* host: padding boxes, packing records (device build) */
+    float    build_s;            /* wall time of the build proper, uploads included */
+    float    device_build_ms;    /* CUDA-event time of sort + clustering + collapse (device build) */
+    uint32_t reserved;
+} OrtBuildStats;
+int ort_scene_build_stats(const OrtScene *scene, OrtBuildStats *out);
+/* copies the flattened tree back (tests: the CUDA build must equal the host execution of the same
+ * algorithm byte for byte); either pointer may be NULL; sizes must match ort_scene_info */
+int ort_scene_download(OrtScene *scene, void *nodes, uint64_t nodes_bytes, void *prims, uint64_t prims_bytes);
 int ort_scene_destroy(OrtScene *scene);
 int ort_scene_info(const OrtScene *scene, OrtSceneInfo *info);
 

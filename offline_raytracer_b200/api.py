@@ -78,6 +78,16 @@ class SceneInfo(C.Structure):
         return d
 
 
+class BuildStats(C.Structure):
+    _fields_ = [("on_device", c_u32), ("ploc_iterations", c_u32), ("wide_depth", c_u32), ("collect_s", c_f),
+                ("prepare_s", c_f), ("build_s", c_f), ("device_build_ms", c_f), ("reserved", c_u32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_[:7]}
+
+
+ORT_BUILD_ON_DEVICE = 1
+
 _lib = None
 
 
@@ -94,6 +104,9 @@ def lib(path=None):
     L.ort_last_error.restype = C.c_char_p
     L.ort_device_count.argtypes = [C.POINTER(C.c_int)]
     L.ort_scene_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    L.ort_scene_create_ex.argtypes = [vp, vp, C.c_int, c_u32, C.POINTER(vp)]
+    L.ort_scene_build_stats.argtypes = [vp, C.POINTER(BuildStats)]
+    L.ort_scene_download.argtypes = [vp, vp, c_u64, vp, c_u64]
     L.ort_scene_destroy.argtypes = [vp]
     L.ort_scene_info.argtypes = [vp, C.POINTER(SceneInfo)]
     L.ort_render_params_default.argtypes = [C.POINTER(RenderParams), c_i32, c_i32, c_u32]
@@ -219,12 +232,33 @@ class HostScene:
 class Scene:
     """Device-resident flattened scene (OrtScene)."""
 
-    def __init__(self, world_ptr, root_ptr, device=0, library=None):
+    def __init__(self, world_ptr, root_ptr, device=0, library=None, build_on_device=None):
+        """build_on_device: True = CUDA builder (ort_scene_create_ex, ORT_BUILD_ON_DEVICE), False = host
+        binned-SAH builder, None = ort_scene_create (host unless ORT_BVH_BUILD=device)"""
         self.L = library or lib()
         h = vp(0)
-        _check(self.L.ort_scene_create(_as_ptr(world_ptr), _as_ptr(root_ptr), device, C.byref(h)), self.L)
+        if build_on_device is None:
+            _check(self.L.ort_scene_create(_as_ptr(world_ptr), _as_ptr(root_ptr), device, C.byref(h)), self.L)
+        else:
+            _check(self.L.ort_scene_create_ex(_as_ptr(world_ptr), _as_ptr(root_ptr), device,
+                                              ORT_BUILD_ON_DEVICE if build_on_device else 0, C.byref(h)), self.L)
         self.h = h
         self.device = device
+
+    def build_stats(self):
+        b = BuildStats()
+        _check(self.L.ort_scene_build_stats(self.h, C.byref(b)), self.L)
+        return b.as_dict()
+
+    def download(self):
+        """(nodes uint8[n, 80], records uint32[m, 12]) of the flattened tree"""
+        i = SceneInfo()
+        _check(self.L.ort_scene_info(self.h, C.byref(i)), self.L)
+        nodes = np.zeros((i.bvh_node_count, i.bvh_node_bytes), np.uint8)
+        kept = i.record_count - i.csg_count
+        prims = np.zeros((kept, 12), np.uint32)
+        _check(self.L.ort_scene_download(self.h, _ptr(nodes), nodes.nbytes, _ptr(prims), prims.nbytes), self.L)
+        return nodes, prims
 
     def close(self):
         if self.h:

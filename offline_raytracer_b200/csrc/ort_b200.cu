@@ -7,8 +7,11 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <algorithm>
 
 #include "wavefront.cuh"
+#include "bvh_build.cuh"
 #include "scene_flatten.h"
 
 using namespace ort;
@@ -53,6 +56,7 @@ struct OrtScene
 {
     int device;
     OrtSceneInfo info;
+    OrtBuildStats build_stats;
     uint32_t main_root, tri_root;
     uint32_t *d_rank_to_prim;
     // device arrays (layout: bvh.h, scene_flatten.h)
@@ -506,13 +510,26 @@ int ort_measure_fp32_peak(int device, float *tflops_non_fma, float *sm_clock_mhz
     return ORT_OK;
 }
 
+static double seconds_since(std::chrono::steady_clock::time_point t0)
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, OrtScene **scene_out)
+{
+    uint32_t flags = 0;
+    if(const char *e = getenv("ORT_BVH_BUILD")) if(!strcmp(e, "device")) flags |= ORT_BUILD_ON_DEVICE;
+    return ort_scene_create_ex(world, top_most_node, device, flags, scene_out);
+}
+
+int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, uint32_t flags, OrtScene **scene_out)
 {
     if(!scene_out) return fail(ORT_ERR_ARG, "scene_out is null");
     *scene_out = 0;
     int n = 0;
     if(ort_device_count(&n) != ORT_OK) return ORT_ERR_CUDA;
     if(device < 0 || device >= n) return fail(ORT_ERR_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
 
     FlatScene flat;
     std::string err;
@@ -520,27 +537,78 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_MERGE_SHAPES")) opt.merge_shapes = atoi(e) != 0;
-    int rc = flatten_scene(world, top_most_node, opt, &flat, &err);
+    const bool on_device = (flags & ORT_BUILD_ON_DEVICE) != 0u;
+    OrtBuildStats bs; memset(&bs, 0, sizeof(bs));
+    bs.on_device = on_device ? 1u : 0u;
+    build::DeviceBuildResult built; memset(&built, 0, sizeof(built));
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<HostPrim> prims;
+    int rc = collect_records(world, top_most_node, &prims, &flat, &err);
     if(rc != ORT_OK) return fail(rc, err);
+    bs.collect_s = (float)seconds_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    if(on_device)
+    {
+        // Morton sort, PLOC clustering and the collapse to 8-wide run as CUDA kernels
+        // (bvh_build.cuh); the host only pads the boxes and packs the records
+        ParallelBuildInput in;
+        rc = prepare_parallel_build(prims, opt, &flat, &in, &err);
+        if(rc != ORT_OK) return fail(rc, err);
+        bs.prepare_s = (float)seconds_since(t0);
+        t0 = std::chrono::steady_clock::now();
+        uint32_t radius = ORT_PLOC_RADIUS;
+        if(const char *e = getenv("ORT_PLOC_RADIUS")) radius = (uint32_t)atoi(e);
+        if(radius < 1u) radius = 1u;
+        if(!build::build_on_device(flat, in, radius, &built, &err)) return fail(ORT_ERR_CUDA, err);
+        flat.wide_depth = std::max(in.sphere_depth, built.depth);
+        if(flat.wide_depth + 2 > ORT_STACK_SIZE)
+        {
+            cudaFree(built.d_nodes); cudaFree(built.d_prims); cudaFree(built.d_rank_to_prim);
+            return fail(ORT_ERR_LIMIT, "wide BVH deeper than the traversal stack");
+        }
+        flat.info.bvh_node_count = built.node_count;
+        flat.info.bvh_node_bytes = (uint32_t)sizeof(WideNode);
+        bs.build_s = (float)seconds_since(t0);
+        bs.device_build_ms = built.build_ms;
+        bs.ploc_iterations = built.ploc_iterations;
+    }
+    else
+    {
+        rc = build_wide_bvh(prims, opt, &flat, &err);
+        if(rc != ORT_OK) return fail(rc, err);
+        bs.build_s = (float)seconds_since(t0);
+    }
+    bs.wide_depth = flat.wide_depth;
 
-    CUDA_TRY(cudaSetDevice(device));
     OrtScene *s = new OrtScene();
     memset(s, 0, sizeof(*s));
     s->device = device;
     s->info = flat.info;
+    s->build_stats = bs;
     s->main_root = flat.main_root;
     s->tri_root = flat.tri_root;
     s->stack_rows = flat.wide_depth + 2u;
-    s->node_count = (uint32_t)flat.nodes.size();
-    s->prim_count = (uint32_t)flat.prims.size();
     s->light_count = (uint32_t)flat.light_is_sphere.size();
     uint64_t total = 0;
-    rc = upload(&s->d_nodes, flat.nodes.data(), flat.nodes.size() * sizeof(WideNode), &total);
-    if(rc == ORT_OK) rc = upload(&s->d_prims, flat.prims.data(), flat.prims.size() * sizeof(PrimRec), &total);
+    if(on_device)
+    {
+        s->node_count = built.node_count; s->prim_count = built.prim_count;
+        s->d_nodes = (q4 *)built.d_nodes; s->d_prims = (q4 *)built.d_prims; s->d_rank_to_prim = built.d_rank_to_prim;
+        total += (uint64_t)built.node_count * sizeof(WideNode) + (uint64_t)built.prim_count * sizeof(PrimRec)
+               + (uint64_t)flat.info.record_count * sizeof(uint32_t);
+        rc = ORT_OK;
+    }
+    else
+    {
+        s->node_count = (uint32_t)flat.nodes.size();
+        s->prim_count = (uint32_t)flat.prims.size();
+        rc = upload(&s->d_nodes, flat.nodes.data(), flat.nodes.size() * sizeof(WideNode), &total);
+        if(rc == ORT_OK) rc = upload(&s->d_prims, flat.prims.data(), flat.prims.size() * sizeof(PrimRec), &total);
+        if(rc == ORT_OK) rc = upload(&s->d_rank_to_prim, flat.rank_to_prim.data(), flat.rank_to_prim.size() * sizeof(uint32_t), &total);
+    }
     if(rc == ORT_OK) rc = upload(&s->d_cyl, flat.cylinders.data(), flat.cylinders.size() * sizeof(CylinderAux), &total);
     if(rc == ORT_OK) rc = upload(&s->d_materials, flat.materials.data(), flat.materials.size() * sizeof(DevMaterial), &total);
     if(rc == ORT_OK) rc = upload(&s->d_light_is_sphere, flat.light_is_sphere.data(), flat.light_is_sphere.size(), &total);
-    if(rc == ORT_OK) rc = upload(&s->d_rank_to_prim, flat.rank_to_prim.data(), flat.rank_to_prim.size() * sizeof(uint32_t), &total);
     if(rc == ORT_OK) rc = upload(&s->d_stats, (const void *)0, 0, &total);
     if(rc != ORT_OK) { ort_scene_destroy(s); return rc; }
     cudaFree(s->d_stats); s->d_stats = 0;
@@ -552,6 +620,30 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
     s->info.device_bytes = total;
     *scene_out = s;
+    return ORT_OK;
+}
+
+int ort_scene_build_stats(const OrtScene *s, OrtBuildStats *out)
+{
+    if(!s || !out) return fail(ORT_ERR_ARG, "null argument");
+    *out = s->build_stats;
+    return ORT_OK;
+}
+
+int ort_scene_download(OrtScene *s, void *nodes, uint64_t nodes_bytes, void *prims, uint64_t prims_bytes)
+{
+    if(!s) return fail(ORT_ERR_ARG, "null scene");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if(nodes)
+    {
+        if(nodes_bytes != (uint64_t)s->node_count * sizeof(WideNode)) return fail(ORT_ERR_ARG, "nodes buffer size mismatch");
+        CUDA_TRY(cudaMemcpy(nodes, s->d_nodes, nodes_bytes, cudaMemcpyDeviceToHost));
+    }
+    if(prims)
+    {
+        if(prims_bytes != (uint64_t)s->prim_count * sizeof(PrimRec)) return fail(ORT_ERR_ARG, "records buffer size mismatch");
+        CUDA_TRY(cudaMemcpy(prims, s->d_prims, prims_bytes, cudaMemcpyDeviceToHost));
+    }
     return ORT_OK;
 }
 

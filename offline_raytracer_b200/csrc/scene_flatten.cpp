@@ -7,12 +7,14 @@
 // is uploaded is rebuilt from the records: binned-SAH binary BVH, collapsed to
 // 8-wide, children placed in octant slots, boxes quantised outward.
 #include "scene_flatten.h"
+#include "bvh_build.h"
 
 #include <math.h>
 #include <string.h>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <chrono>
 #include <deque>
 #include <mutex>
 #include <thread>
@@ -429,6 +431,43 @@ inline int grid_exponent(double extent)
 
 namespace {
 
+// the 48-byte device record of one primitive (bvh.h); a cylinder also gets its CylinderAux entry
+PrimRec make_record(const HostPrim &hp, FlatScene *out)
+{
+    PrimRec r; memset(&r, 0, sizeof(r));
+    r.rank = hp.rank; r.mat = hp.mat;
+    r.ax = hp.a.x; r.ay = hp.a.y; r.az = hp.a.z;
+    switch(hp.kind)
+    {
+        case PRIM_TRIANGLE:
+            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z;
+            r.cx = hp.c.x; r.cy = hp.c.y; r.cz = hp.c.z;
+            r.kind = PRIM_TRIANGLE;
+            break;
+        case PRIM_SPHERE:
+            r.bx = hp.radius; r.kind = PRIM_SPHERE;
+            break;
+        case PRIM_AAB:
+            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z; r.kind = PRIM_AAB;
+            break;
+        case PRIM_CYLINDER:
+        {
+            CylinderAux ca; memset(&ca, 0, sizeof(ca));
+            exact::m3 rot = exact::rotation_matrix_along_z(hp.b);     // ray.cpp:295
+            ca.base[0] = hp.a.x; ca.base[1] = hp.a.y; ca.base[2] = hp.a.z;
+            ca.axis_len = length(hp.b);                               // ray.cpp:302
+            ca.radius = hp.radius;
+            ca.r0[0] = rot.r0.x; ca.r0[1] = rot.r0.y; ca.r0[2] = rot.r0.z;
+            ca.r1[0] = rot.r1.x; ca.r1[1] = rot.r1.y; ca.r1[2] = rot.r1.z;
+            ca.r2[0] = rot.r2.x; ca.r2[1] = rot.r2.y; ca.r2[2] = rot.r2.z;
+            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z;
+            r.kind = PRIM_CYLINDER | ((uint32_t)out->cylinders.size() << 8);
+            out->cylinders.push_back(ca);
+        } break;
+    }
+    return r;
+}
+
 // builds one wide tree over `prims` and appends it to out->nodes / prims /
 // cylinders; the tree's root is the first node appended
 int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out,
@@ -445,8 +484,12 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
         return ORT_OK;
     }
 
+    const bool timing = getenv("ORT_TIMING") != 0;
+    auto t0 = std::chrono::steady_clock::now();
     Builder b(prims, opt);
     b.build();
+    auto t1 = std::chrono::steady_clock::now();
+    if(timing) fprintf(stderr, "[ort] binned-SAH build of %zu records: %.2f s\n", prims.size(), std::chrono::duration<double>(t1 - t0).count());
 
     struct WItem { uint32_t b2; uint32_t depth; };
     std::deque<WItem> queue;
@@ -565,37 +608,7 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
                 {
                     const HostPrim &hp = prims[b.idx[c.first + i]];
                     if(hp.kind != PRIM_TRIANGLE) only_triangles = false;
-                    PrimRec r; memset(&r, 0, sizeof(r));
-                    r.rank = hp.rank; r.mat = hp.mat;
-                    r.ax = hp.a.x; r.ay = hp.a.y; r.az = hp.a.z;
-                    switch(hp.kind)
-                    {
-                        case PRIM_TRIANGLE:
-                            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z;
-                            r.cx = hp.c.x; r.cy = hp.c.y; r.cz = hp.c.z;
-                            r.kind = PRIM_TRIANGLE;
-                            break;
-                        case PRIM_SPHERE:
-                            r.bx = hp.radius; r.kind = PRIM_SPHERE;
-                            break;
-                        case PRIM_AAB:
-                            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z; r.kind = PRIM_AAB;
-                            break;
-                        case PRIM_CYLINDER:
-                        {
-                            CylinderAux ca; memset(&ca, 0, sizeof(ca));
-                            exact::m3 rot = exact::rotation_matrix_along_z(hp.b);     // ray.cpp:295
-                            ca.base[0] = hp.a.x; ca.base[1] = hp.a.y; ca.base[2] = hp.a.z;
-                            ca.axis_len = length(hp.b);                               // ray.cpp:302
-                            ca.radius = hp.radius;
-                            ca.r0[0] = rot.r0.x; ca.r0[1] = rot.r0.y; ca.r0[2] = rot.r0.z;
-                            ca.r1[0] = rot.r1.x; ca.r1[1] = rot.r1.y; ca.r1[2] = rot.r1.z;
-                            ca.r2[0] = rot.r2.x; ca.r2[1] = rot.r2.y; ca.r2[2] = rot.r2.z;
-                            r.bx = hp.b.x; r.by = hp.b.y; r.bz = hp.b.z;
-                            r.kind = PRIM_CYLINDER | ((uint32_t)out->cylinders.size() << 8);
-                            out->cylinders.push_back(ca);
-                        } break;
-                    }
+                    PrimRec r = make_record(hp, out);
                     out->prims.push_back(r);
                 }
                 prim_off += c.count;
@@ -607,19 +620,19 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
     }
 
     *depth_out = wide_depth;
+    if(timing) fprintf(stderr, "[ort] collapse to 8-wide + quantise + emit: %.2f s\n",
+                       std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     return ORT_OK;
 }
 
 } // namespace
 
-int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, std::string *err)
+// pads the primitive boxes (see bvh.h: conservative culling) and separates the spheres, which get
+// a tree of their own, from the rest
+static int pad_and_split(std::vector<HostPrim> &prims, const BuildOptions &opt,
+                         std::vector<HostPrim> *spheres, std::vector<HostPrim> *shapes, std::vector<HostPrim> *tris, std::string *err)
 {
-    out->nodes.clear(); out->prims.clear(); out->cylinders.clear();
-    out->wide_depth = 0;
-    out->main_root = 0;
     if(opt.max_leaf < 1 || opt.max_leaf > 3) { *err = "max_leaf must be 1..3"; return ORT_ERR_ARG; }
-
-    // pad the primitive boxes (see bvh.h: conservative culling)
     double scene_abs = 0.0;
     for(size_t i = 0; i < prims.size(); ++i)
         for(int k = 0; k < 3; ++k)
@@ -627,7 +640,6 @@ int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatSc
             scene_abs = std::max(scene_abs, fabs((double)prims[i].lo[k]));
             scene_abs = std::max(scene_abs, fabs((double)prims[i].hi[k]));
         }
-    std::vector<HostPrim> spheres, shapes, tris;
     for(size_t i = 0; i < prims.size(); ++i)
     {
         HostPrim &p = prims[i];
@@ -653,35 +665,17 @@ int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatSc
             p.lo[k] = nextafterf((float)((double)p.lo[k] - pad), -INFINITY);
             p.hi[k] = nextafterf((float)((double)p.hi[k] + pad), INFINITY);
         }
-        if(p.kind == PRIM_SPHERE) spheres.push_back(p);
-        else if(p.kind == PRIM_TRIANGLE || opt.merge_shapes) tris.push_back(p);
-        else shapes.push_back(p);
+        if(p.kind == PRIM_SPHERE) spheres->push_back(p);
+        else if(p.kind == PRIM_TRIANGLE || opt.merge_shapes) tris->push_back(p);
+        else shapes->push_back(p);
     }
     std::vector<HostPrim>().swap(prims);
-    out->prims.reserve(spheres.size() + shapes.size() + tris.size());
+    return ORT_OK;
+}
 
-    // Three trees share the node array, in this order:
-    //   [0, main_root)         spheres            -- traversed UNCLIPPED (see above)
-    //   [main_root, tri_root)  boxes + cylinders  -- the few analytic shapes; typically the room
-    //   [tri_root, ...)        triangles
-    // so the kind of a leaf's records follows from the node index, primitive tests of one kind
-    // run together, and the shapes (tested first) give an early bound that clips the triangles.
-    uint32_t d0 = 0, d1 = 0, d2 = 0;
-    if(!spheres.empty())
-    {
-        int rc = emit_tree(spheres, opt, out, &d0, err);
-        if(rc != ORT_OK) return rc;
-    }
-    out->main_root = (uint32_t)out->nodes.size();
-    if(!shapes.empty())
-    {
-        int rc = emit_tree(shapes, opt, out, &d1, err);
-        if(rc != ORT_OK) return rc;
-    }
-    out->tri_root = (uint32_t)out->nodes.size();
-    int rc = emit_tree(tris, opt, out, &d2, err);
-    if(rc != ORT_OK) return rc;
-    out->wide_depth = std::max(d0, std::max(d1, d2));
+static int finish_flat_scene(FlatScene *out, uint32_t depth, std::string *err)
+{
+    out->wide_depth = depth;
     // every level pushes at most one pending node group; +2 for the other trees' root entries
     if(out->wide_depth + 2 > ORT_STACK_SIZE)
     {
@@ -695,6 +689,168 @@ int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatSc
     out->info.bvh_node_count = (uint32_t)out->nodes.size();
     out->info.bvh_node_bytes = (uint32_t)sizeof(WideNode);
     return ORT_OK;
+}
+
+int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, std::string *err)
+{
+    out->nodes.clear(); out->prims.clear(); out->cylinders.clear();
+    out->wide_depth = 0;
+    out->main_root = 0;
+    std::vector<HostPrim> spheres, shapes, tris;
+    int rc = pad_and_split(prims, opt, &spheres, &shapes, &tris, err);
+    if(rc != ORT_OK) return rc;
+    out->prims.reserve(spheres.size() + shapes.size() + tris.size());
+
+    // Three trees share the node array, in this order:
+    //   [0, main_root)         spheres            -- traversed UNCLIPPED (see above)
+    //   [main_root, tri_root)  boxes + cylinders  -- the few analytic shapes; typically the room
+    //   [tri_root, ...)        triangles
+    // so the kind of a leaf's records follows from the node index, primitive tests of one kind
+    // run together, and the shapes (tested first) give an early bound that clips the triangles.
+    uint32_t d0 = 0, d1 = 0, d2 = 0;
+    if(!spheres.empty())
+    {
+        rc = emit_tree(spheres, opt, out, &d0, err);
+        if(rc != ORT_OK) return rc;
+    }
+    out->main_root = (uint32_t)out->nodes.size();
+    if(!shapes.empty())
+    {
+        rc = emit_tree(shapes, opt, out, &d1, err);
+        if(rc != ORT_OK) return rc;
+    }
+    out->tri_root = (uint32_t)out->nodes.size();
+    rc = emit_tree(tris, opt, out, &d2, err);
+    if(rc != ORT_OK) return rc;
+    return finish_flat_scene(out, std::max(d0, std::max(d1, d2)), err);
+}
+
+// ---- the data-parallel builder (bvh_build.h) ---------------------------------------------------------
+// Common preparation for its host and CUDA executions: the sphere tree is built here (analytic
+// shapes are few); everything else -- triangles, boxes, cylinders: one tree -- is handed over as
+// flat arrays in input order.
+int prepare_parallel_build(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, ParallelBuildInput *in, std::string *err)
+{
+    out->nodes.clear(); out->prims.clear(); out->cylinders.clear();
+    out->wide_depth = 0;
+    out->main_root = 0;
+    BuildOptions o = opt; o.merge_shapes = true;
+    std::vector<HostPrim> spheres, shapes, rest;
+    int rc = pad_and_split(prims, o, &spheres, &shapes, &rest, err);
+    if(rc != ORT_OK) return rc;
+    in->sphere_depth = 0;
+    if(!spheres.empty())
+    {
+        rc = emit_tree(spheres, o, out, &in->sphere_depth, err);
+        if(rc != ORT_OK) return rc;
+    }
+    out->main_root = out->tri_root = (uint32_t)out->nodes.size();
+    in->max_leaf = o.max_leaf;
+    in->traversal_cost = o.traversal_cost;
+    in->boxes.resize(6 * rest.size());
+    in->recs.resize(rest.size());
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for(size_t i = 0; i < rest.size(); ++i)
+    {
+        for(int k = 0; k < 3; ++k)
+        {
+            in->boxes[6 * i + k] = rest[i].lo[k]; in->boxes[6 * i + 3 + k] = rest[i].hi[k];
+            double c = 0.5 * ((double)rest[i].lo[k] + (double)rest[i].hi[k]);
+            lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c);
+        }
+        in->recs[i] = make_record(rest[i], out);
+    }
+    for(int k = 0; k < 3; ++k)
+    {
+        in->scene_lo[k] = rest.empty() ? 0.0 : lo[k];
+        double ext = rest.empty() ? 0.0 : hi[k] - lo[k];
+        in->scene_scale[k] = ext > 0.0 ? 2097152.0 / ext : 0.0;
+    }
+    return ORT_OK;
+}
+
+// Host execution of bvh_build.h: plain loops over the same per-element functions the CUDA kernels
+// call, in the same order.  Test infrastructure (tests/sim): it pins what the kernels must produce.
+int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOptions &opt, uint32_t radius, FlatScene *out, std::string *err)
+{
+    using namespace build;
+    ParallelBuildInput in;
+    int rc = prepare_parallel_build(prims, opt, out, &in, err);
+    if(rc != ORT_OK) return rc;
+    const uint32_t n = (uint32_t)in.recs.size();
+    const uint32_t node_offset = (uint32_t)out->nodes.size(), prim_offset = (uint32_t)out->prims.size();
+    uint32_t depth = 0;
+    if(n == 0)
+    {
+        WideNode e; memset(&e, 0, sizeof(e));
+        e.ex = e.ey = e.ez = 127;
+        for(int s = 0; s < 8; ++s) { e.qlo_x[s] = e.qlo_y[s] = e.qlo_z[s] = 255; }
+        out->nodes.push_back(e);
+        return finish_flat_scene(out, std::max(in.sphere_depth, 1u), err);
+    }
+    // 1. Morton order
+    std::vector<uint64_t> code(n);
+    std::vector<uint32_t> order(n);
+    for(uint32_t i = 0; i < n; ++i) { code[i] = morton63(&in.boxes[6 * i], &in.boxes[6 * i + 3], in.scene_lo, in.scene_scale); order[i] = i; }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return code[a] < code[b]; });
+    // 2. PLOC
+    std::vector<B2> nodes(2 * (size_t)n);
+    std::vector<uint32_t> sizes(2 * (size_t)n, 0u), cluster(n), next_cluster(n), nn(n), fate(n);
+    std::vector<float> cost(2 * (size_t)n, 0.f);
+    for(uint32_t i = 0; i < n; ++i)
+    {
+        B2 l; uint32_t src = order[i];
+        for(int k = 0; k < 3; ++k) { l.lo[k] = in.boxes[6 * src + k]; l.hi[k] = in.boxes[6 * src + 3 + k]; }
+        l.left = B2_LEAF; l.right = src;
+        nodes[i] = l; sizes[i] = 1u | B2_LEAF_FLAG; cost[i] = (float)half_area(l); cluster[i] = i;
+    }
+    uint32_t count = n, next_node = n;
+    while(count > 1)
+    {
+        for(uint32_t i = 0; i < count; ++i) nn[i] = ploc_nearest(i, count, cluster.data(), nodes.data(), radius);
+        for(uint32_t i = 0; i < count; ++i) fate[i] = ploc_fate(i, nn.data());
+        uint32_t pos = 0, mid = 0;
+        for(uint32_t i = 0; i < count; ++i)
+        {
+            ploc_apply(i, nn.data(), cluster.data(), fate[i], pos, mid, next_node, nodes.data(), sizes.data(), cost.data(), next_cluster.data(),
+                       in.max_leaf, in.traversal_cost);
+            pos += fate[i] != 0u; mid += fate[i] == 2u;
+        }
+        next_node += mid; count = pos;
+        cluster.swap(next_cluster);
+    }
+    const uint32_t root = cluster[0];
+    // 3. collapse, level by level
+    out->nodes.resize(node_offset + 1);
+    out->prims.resize(prim_offset + n);
+    std::vector<Item> items(1), next_items;
+    items[0].b2 = root; items[0].wide = node_offset;
+    uint32_t node_count = node_offset + 1, prim_count = prim_offset;
+    std::vector<Kids> kids;
+    while(!items.empty())
+    {
+        ++depth;
+        kids.resize(items.size());
+        uint32_t total_inner = 0, total_prims = 0;
+        for(size_t i = 0; i < items.size(); ++i)
+        {
+            gather_kids(items[i].b2, nodes.data(), sizes.data(), in.max_leaf, &kids[i]);
+            total_inner += kids[i].n_inner; total_prims += kids[i].n_prims;
+        }
+        out->nodes.resize(node_count + total_inner);
+        next_items.resize(total_inner);
+        uint32_t run_inner = 0, run_prims = 0;
+        for(size_t i = 0; i < items.size(); ++i)
+        {
+            emit_wide(kids[i], items[i].wide, node_count + run_inner, prim_count + run_prims, run_inner,
+                      nodes.data(), sizes.data(), in.max_leaf, in.recs.data(), out->nodes.data(), out->prims.data(), next_items.data());
+            run_inner += kids[i].n_inner; run_prims += kids[i].n_prims;
+        }
+        node_count += total_inner; prim_count += total_prims;
+        items.swap(next_items);
+    }
+    if(prim_count != prim_offset + n) { *err = "internal: parallel build lost records"; return ORT_ERR_LIMIT; }
+    return finish_flat_scene(out, std::max(in.sphere_depth, depth), err);
 }
 
 } // namespace ort

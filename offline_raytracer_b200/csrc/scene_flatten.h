@@ -70,6 +70,20 @@ int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
 // build the wide BVH over `prims` (consumed) into out->nodes / prims / cylinders
 int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, std::string *err);
 
+// ---- the data-parallel builder (bvh_build.h; CUDA execution in bvh_build.cuh) ----
+struct ParallelBuildInput
+{
+    std::vector<float> boxes;        // 6 floats per primitive: padded lo, hi -- input order
+    std::vector<PrimRec> recs;       // the device records, input order
+    double scene_lo[3], scene_scale[3];   // box-centre bounds -> 21-bit grid
+    uint32_t max_leaf;
+    float traversal_cost;
+    uint32_t sphere_depth;           // depth of the sphere tree already emitted into the FlatScene
+};
+int prepare_parallel_build(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, ParallelBuildInput *in, std::string *err);
+int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOptions &opt, uint32_t radius, FlatScene *out, std::string *err);
+#define ORT_PLOC_RADIUS 16u
+
 inline int flatten_scene(const OrtWorld *world, const OrtBVHOctreeNode *root, const BuildOptions &opt,
                          FlatScene *out, std::string *err)
 {

@@ -40,6 +40,32 @@ void *sim_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *root, floa
     s->view.tri_root = s->flat.tri_root;
     return s;
 }
+// the same scene through the data-parallel builder (bvh_build.h), executed on the host
+void *sim_scene_create_parallel(const OrtWorld *world, const OrtBVHOctreeNode *root, uint32_t radius)
+{
+    SimScene *s = new SimScene();
+    BuildOptions opt;
+    std::string err;
+    std::vector<HostPrim> prims;
+    int rc = collect_records(world, root, &prims, &s->flat, &err);
+    if(rc == ORT_OK) rc = build_wide_bvh_parallel_host(prims, opt, radius ? radius : ORT_PLOC_RADIUS, &s->flat, &err);
+    if(rc != ORT_OK)
+    {
+        fprintf(stderr, "sim_scene_create_parallel: %s\n", err.c_str());
+        delete s; return 0;
+    }
+    s->view.nodes = (const q4 *)s->flat.nodes.data();
+    s->view.prims = (const q4 *)s->flat.prims.data();
+    s->view.cyl = (const q4 *)s->flat.cylinders.data();
+    s->view.node_count = (uint32_t)s->flat.nodes.size();
+    s->view.prim_count = (uint32_t)s->flat.prims.size();
+    s->view.main_root = s->flat.main_root;
+    s->view.tri_root = s->flat.tri_root;
+    return s;
+}
+// raw bytes of the flattened tree, for byte-for-byte comparison with the CUDA execution
+uint64_t sim_scene_nodes(void *h, const void **p) { SimScene *s = (SimScene *)h; *p = s->flat.nodes.data(); return s->flat.nodes.size() * sizeof(WideNode); }
+uint64_t sim_scene_prims(void *h, const void **p) { SimScene *s = (SimScene *)h; *p = s->flat.prims.data(); return s->flat.prims.size() * sizeof(PrimRec); }
 void sim_scene_destroy(void *h) { delete (SimScene *)h; }
 void sim_scene_info(void *h, OrtSceneInfo *info, uint32_t *wide_depth) { *info = ((SimScene *)h)->flat.info; *wide_depth = ((SimScene *)h)->flat.wide_depth; }
 
