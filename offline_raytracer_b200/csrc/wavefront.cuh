@@ -42,7 +42,7 @@ enum { WF_DEAD = 0u, WF_ACTIVE = 1u, WF_FRESH = 2u };
 struct WfBuffers
 {
     float4 *rec;         // WF_REC_QUADS quads per slot
-    uint32_t *key;       // shading key written by EXTEND: primary << 8 | min(material, 255); 511 = dead
+    uint32_t *key;       // shading key written by EXTEND: primary << 8 | min(material, 254); 511 = dead (so 256 | 255 must never be a live key)
     uint32_t *perm;      // slots grouped by key (counting sort)
     uint32_t capacity;
 };
@@ -171,7 +171,7 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
                 uint32_t mat = 0u;
                 if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
                 wf_store_hit(wf, slot, t.best_t, t.best_prim, mat);
-                uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
+                uint32_t key = (is_primary ? 256u : 0u) | (mat < 254u ? mat : 254u);
                 wf.key[slot] = key;
                 atomicAdd(&sh_hist[key], 1u);
                 has_ray = false;
@@ -352,7 +352,7 @@ k_wf_extend_v(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned l
             uint32_t mat = 0u;
             if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
             wf_store_hit(wf, slot, t.best_t, t.best_prim, mat);
-            uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
+            uint32_t key = (is_primary ? 256u : 0u) | (mat < 254u ? mat : 254u);
             wf.key[slot] = key;
             atomicAdd(&sh_hist[key], 1u);
             has_ray = false;
@@ -570,7 +570,7 @@ k_wf_extend_q(SceneView scene, WfBuffers wf, const uint32_t *__restrict__ rank_t
                 mat = f2u(ldq(scene.prims + 3u * prim + 1u).w);
             }
             wf_store_hit(wf, slot, __uint_as_float((uint32_t)(best >> 32)), prim, mat);
-            uint32_t key = (is_primary ? 256u : 0u) | (mat < 255u ? mat : 255u);
+            uint32_t key = (is_primary ? 256u : 0u) | (mat < 254u ? mat : 254u);
             wf.key[slot] = key;
             atomicAdd(&sh_hist[key], 1u);
             has_ray = false;

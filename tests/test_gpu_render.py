@@ -243,3 +243,31 @@ def test_hdr_written_from_the_device_is_byte_identical(ort, testscene_host, tmp_
     want = np.array([[ort.v3_to_rgbe(px[63 - r, x]) for x in range(96)] for r in range(64)], np.uint32)
     assert np.array_equal(got, want)
     sc.close()
+
+
+def test_more_than_255_materials(ort, tmp_path):
+    """the shading key keeps 8 bits of the material index: indices >= 254 share a bin, and a primary
+    ray hitting one must not land in the bin reserved for dead slots (it did: key 256 | 255 = 511, the
+    slot was never shaded again and the render ended early -- found on the 729-material scene of
+    BASELINE config 5).  Wavefront == megakernel, and every sample is taken."""
+    rng = np.random.default_rng(3)
+    lines = ["screen 160 90", "camera 0.35 0.3 5.0 b 0.35 q 1.0 0.0 0.0 0.0", "ambient 0.1 0.1 0.1", "",
+             "brdf 0.7 0.7 0.7 0.0 0.0 0.0 10 0.0 0.0 0.0 1.0",
+             "box -3.1 -2.1 -3.1 6.2 0.1 9.2", "box -3.1 2.0 -3.1 6.2 0.1 9.2", "box -3.1 -2.1 -3.1 6.2 4.2 0.1",
+             "box -3.1 -2.1 6.0 6.2 4.2 0.1", "box -3.1 -2.1 -3.1 0.1 4.2 9.2", "box 3.0 -2.1 -3.1 0.1 4.2 9.2"]
+    for i in range(300):          # 300 more materials, one small box each, spread over the back of the room
+        c = rng.uniform(0.2, 0.9, 3)
+        x, y = -2.8 + 0.28 * (i % 20), -1.9 + 0.25 * (i // 20)
+        lines += ["brdf %.3f %.3f %.3f 0.0 0.0 0.0 10 0.0 0.0 0.0 1.0" % tuple(c), "box %.3f %.3f -2.5 0.2 0.2 0.2" % (x, y)]
+    lines += ["light 6.0 6.0 6.0", "sphere 0.0 1.4 1.0 0.4", ""]
+    path = tmp_path / "many_materials.scn"
+    path.write_text("\n".join(lines))
+    W2, H2, SPP = 160, 90, 8
+    hs = ort.HostScene.load(str(path), str(tmp_path), W2, H2)
+    sc = ort.Scene(hs.world, hs.root, 0)
+    assert sc.info()["material_count"] > 300
+    a, sa = sc.render(hs.camera, ort.default_params(W2, H2, SPP, chunk_spp=4, kernel=ort.ORT_KERNEL_MEGAKERNEL))
+    b, sb = sc.render(hs.camera, ort.default_params(W2, H2, SPP, chunk_spp=4, kernel=ort.ORT_KERNEL_WAVEFRONT))
+    assert sa["samples"] == sb["samples"] == W2 * H2 * SPP and sa["rays"] == sb["rays"]
+    assert np.array_equal(bits(a), bits(b))
+    sc.close()

@@ -57,7 +57,7 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     hs = ort.HostScene.load(a.scene, a.base, 1920, 1080)
-    sc = ort.Scene(hs.world, hs.root, 0)
+    sc = ort.Scene(hs.world, hs.root, 0)          # ORT_BVH_BUILD=device selects the CUDA builder
     info = sc.info()
     st = torch.cuda.current_stream().cuda_stream
     out = {"scene": os.path.basename(a.scene), "triangles": info["triangle_count"], "bvh_nodes": info["bvh_node_count"], "n": a.n}

@@ -17,9 +17,20 @@ ap.add_argument("--chunk", type=int, default=16)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--kernel", type=int, default=0)
 ap.add_argument("--lib", default="")
+ap.add_argument("--build", default="", help="host | device (default: ort_scene_create's choice)")
 a = ap.parse_args()
+import time
+t0 = time.time()
 hs = ort.HostScene.load(a.scene, a.base, a.width, a.height)
-sc = ort.Scene(hs.world, hs.root, 0, library=ort.lib(os.path.abspath(a.lib)) if a.lib else None)
+t1 = time.time()
+sc = ort.Scene(hs.world, hs.root, 0, library=ort.lib(os.path.abspath(a.lib)) if a.lib else None,
+               build_on_device={"": None, "host": False, "device": True}[a.build])
+t2 = time.time()
+inf, bs = sc.info(), sc.build_stats()
+print("load %.2f s | scene_create %.2f s: collect %.2f prepare %.2f build %.2f (device kernels %.1f ms, %d PLOC rounds) | "
+      "%d triangles, %d wide nodes, depth %d, %.1f MB on device" % (
+          t1 - t0, t2 - t1, bs["collect_s"], bs["prepare_s"], bs["build_s"], bs["device_build_ms"], bs["ploc_iterations"],
+          inf["triangle_count"], inf["bvh_node_count"], bs["wide_depth"], inf["device_bytes"] / 1e6))
 P = ort.default_params(a.width, a.height, a.spp, chunk_spp=a.chunk, kernel=a.kernel)
 for _ in range(a.reps):
     img, st = sc.render(hs.camera, P)
