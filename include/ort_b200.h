@@ -96,6 +96,30 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
 int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node,
                         int device, uint32_t flags, OrtScene **scene_out);
 
+/* Scene hand-off WITHOUT the octree.  The reference builds its octree only to have
+ * something to traverse; this library rebuilds the acceleration structure anyway and needs from the
+ * octree nothing but each record's RANK -- its position in the order raycast_bvh would test records
+ * with no culling (breadth-first over nodes, push-buffer order within a node), which breaks exact-t
+ * ties.  That order is a pure function of the shape lists: push_shape_inside_node (ray.cpp:1799-1948)
+ * sends a shape down the octant of its box centre until it is alone in a node or depth 10 is reached,
+ * so a record's node is the shortest prefix of its 10-digit octant path that no other record shares,
+ * and the rank order is "sort by (depth, path prefix, insertion index)".  ort_scene_create_from_lists
+ * computes exactly that with two radix sorts instead of minutes of pointer-chasing inserts; the
+ * resulting scene is identical to ort_scene_create on the octree the reference would have built
+ * (tests/test_host_scene.py).  Lists are in the reference's insertion order (macos_main.mm:474-538):
+ * triangles of mesh 0, 1, ..., then cylinders, boxes, spheres, then the inert CSG record if any. */
+typedef struct OrtShapeLists
+{
+    const OrtMesh     *meshes;    uint32_t mesh_count;
+    const OrtCylinder *cylinders; uint32_t cylinder_count;
+    const OrtAAB      *boxes;     uint32_t box_count;
+    const OrtSphere   *spheres;   uint32_t sphere_count;
+    const OrtCSG      *csg;                 /* NULL, or the one hard-coded record (macos_main.mm:322-332) */
+    ort_v3 root_min, root_max;              /* box of the top-most node (macos_main.mm:421-472) */
+} OrtShapeLists;
+int ort_scene_create_from_lists(const OrtWorld *world, const OrtShapeLists *lists,
+                                int device, uint32_t flags, OrtScene **scene_out);
+
 typedef struct OrtBuildStats
 {
     uint32_t on_device;          /* 1 = built by the CUDA kernels */
@@ -261,6 +285,10 @@ const OrtWorld *ort_host_scene_world(const OrtHostScene *hs);
 const OrtCamera *ort_host_scene_camera(const OrtHostScene *hs);
 const OrtBVHOctreeNode *ort_host_scene_root(const OrtHostScene *hs);
 const OrtMesh *ort_host_scene_meshes(const OrtHostScene *hs, uint32_t *mesh_count);
+/* the shape lists of the loaded scene, for ort_scene_create_from_lists; with_csg & ORT_HOST_NO_OCTREE
+ * makes ort_host_scene_load skip the octree (ort_host_scene_root then returns NULL) */
+#define ORT_HOST_NO_OCTREE 2
+int ort_host_scene_lists(const OrtHostScene *hs, OrtShapeLists *out);
 /* mesh loader alone; vertices (xyz floats) and indices are malloc'd, free with ort_free */
 int ort_load_mesh(const char *path, float **vertices, uint32_t *vertex_count,
                   uint32_t **indices, uint32_t *index_count);

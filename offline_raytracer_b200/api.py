@@ -78,6 +78,15 @@ class SceneInfo(C.Structure):
         return d
 
 
+class ShapeLists(C.Structure):
+    _fields_ = [("meshes", vp), ("mesh_count", c_u32), ("cylinders", vp), ("cylinder_count", c_u32),
+                ("boxes", vp), ("box_count", c_u32), ("spheres", vp), ("sphere_count", c_u32),
+                ("csg", vp), ("root_min", V3), ("root_max", V3)]
+
+
+ORT_HOST_NO_OCTREE = 2
+
+
 class BuildStats(C.Structure):
     _fields_ = [("on_device", c_u32), ("ploc_iterations", c_u32), ("wide_depth", c_u32), ("collect_s", c_f),
                 ("prepare_s", c_f), ("build_s", c_f), ("device_build_ms", c_f), ("reserved", c_u32)]
@@ -105,6 +114,7 @@ def lib(path=None):
     L.ort_device_count.argtypes = [C.POINTER(C.c_int)]
     L.ort_scene_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
     L.ort_scene_create_ex.argtypes = [vp, vp, C.c_int, c_u32, C.POINTER(vp)]
+    L.ort_scene_create_from_lists.argtypes = [vp, C.POINTER(ShapeLists), C.c_int, c_u32, C.POINTER(vp)]
     L.ort_scene_build_stats.argtypes = [vp, C.POINTER(BuildStats)]
     L.ort_scene_download.argtypes = [vp, vp, c_u64, vp, c_u64]
     L.ort_scene_destroy.argtypes = [vp]
@@ -212,13 +222,23 @@ class HostScene:
         self.root = L.ort_host_scene_root(handle)
 
     @classmethod
-    def load(cls, scn_path, base_dir, width, height, with_csg=True):
+    def load(cls, scn_path, base_dir, width, height, with_csg=True, octree=True):
+        """octree=False skips the reference's octree (root is then None): for Scene.from_lists"""
         L = lib()
         if not base_dir.endswith("/"):
             base_dir += "/"
         h = vp(0)
-        _check(L.ort_host_scene_load(scn_path.encode(), base_dir.encode(), width, height, int(with_csg), C.byref(h)))
+        flags = (1 if with_csg else 0) | (0 if octree else ORT_HOST_NO_OCTREE)
+        _check(L.ort_host_scene_load(scn_path.encode(), base_dir.encode(), width, height, flags, C.byref(h)))
         return cls(h, width, height)
+
+    def lists(self):
+        """the scene's shape lists in the reference's insertion order (OrtShapeLists)"""
+        L = lib()
+        L.ort_host_scene_lists.argtypes = [vp, C.POINTER(ShapeLists)]
+        out = ShapeLists()
+        _check(L.ort_host_scene_lists(self.h, C.byref(out)))
+        return out
 
     def camera_array(self):
         return np.ctypeslib.as_array(C.cast(self.camera, C.POINTER(c_f)), shape=(12,)).copy()
@@ -244,6 +264,18 @@ class Scene:
                                               ORT_BUILD_ON_DEVICE if build_on_device else 0, C.byref(h)), self.L)
         self.h = h
         self.device = device
+
+    @classmethod
+    def from_lists(cls, world_ptr, lists, device=0, build_on_device=False, library=None):
+        """ort_scene_create_from_lists: no octree needed; `lists` is a ShapeLists (HostScene.lists())"""
+        self = cls.__new__(cls)
+        self.L = library or lib()
+        h = vp(0)
+        _check(self.L.ort_scene_create_from_lists(_as_ptr(world_ptr), C.byref(lists), device,
+                                                  ORT_BUILD_ON_DEVICE if build_on_device else 0, C.byref(h)), self.L)
+        self.h = h
+        self.device = device
+        return self
 
     def build_stats(self):
         b = BuildStats()

@@ -275,7 +275,8 @@ int assemble_scene(const char *scn_path, const char *base_dir, int32_t width, in
     sc.output_height = height;
 
     // hard-coded, inert CSG (macos_main.mm:322-332); it occupies a rank
-    hs->has_csg = with_csg != 0;
+    const bool build_octree = (with_csg & ORT_HOST_NO_OCTREE) == 0;
+    hs->has_csg = (with_csg & 1) != 0;
     memset(&hs->csg, 0, sizeof(hs->csg));
     if(hs->has_csg)
     {
@@ -365,6 +366,10 @@ int assemble_scene(const char *scn_path, const char *base_dir, int32_t width, in
     }
     f3 root_center = 0.5f * (V(root->aabb_min) + V(root->aabb_max));
     f3 root_half = V(root->aabb_max) - root_center;
+    hs->root_min = root->aabb_min; hs->root_max = root->aabb_max;
+    hs->top_most_node = 0;
+    if(build_octree)
+    {
 
     // insertion (macos_main.mm:474-538), depth 10
     OctreeBuilder ob; ob.hs = hs; ob.desired_depth = 10;
@@ -388,6 +393,7 @@ int assemble_scene(const char *scn_path, const char *base_dir, int32_t width, in
     size_t cursor = 0;
     ob.compact(root, &cursor);
     hs->top_most_node = root;
+    }
 
     // camera (macos_main.mm:548-556): axes pre-scaled by the image-plane extents
     hs->camera.p = sc.camera_p;
@@ -481,6 +487,20 @@ const OrtMesh *ort_host_scene_meshes(const OrtHostScene *hs, uint32_t *mesh_coun
 {
     if(mesh_count) *mesh_count = hs ? (uint32_t)hs->meshes.size() : 0;
     return hs && !hs->meshes.empty() ? hs->meshes.data() : 0;
+}
+
+int ort_host_scene_lists(const OrtHostScene *hs, OrtShapeLists *out)
+{
+    if(!hs || !out) { ort_set_last_error_("null argument"); return ORT_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    const ort::ParsedScene &sc = hs->parsed;
+    out->meshes = hs->meshes.empty() ? 0 : hs->meshes.data(); out->mesh_count = (uint32_t)hs->meshes.size();
+    out->cylinders = sc.cylinders.empty() ? 0 : sc.cylinders.data(); out->cylinder_count = (uint32_t)sc.cylinders.size();
+    out->boxes = sc.boxes.empty() ? 0 : sc.boxes.data(); out->box_count = (uint32_t)sc.boxes.size();
+    out->spheres = sc.spheres.empty() ? 0 : sc.spheres.data(); out->sphere_count = (uint32_t)sc.spheres.size();
+    out->csg = hs->has_csg ? &hs->csg : 0;
+    out->root_min = hs->root_min; out->root_max = hs->root_max;
+    return ORT_OK;
 }
 
 int ort_load_mesh(const char *path, float **vertices, uint32_t *vertex_count, uint32_t **indices, uint32_t *index_count)

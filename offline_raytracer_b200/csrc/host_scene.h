@@ -65,6 +65,7 @@ struct OrtHostScene
     OrtCSG csg;
     bool has_csg;
     uint32_t node_count;
+    ort_v3 root_min, root_max;                              // box of the top-most node (macos_main.mm:421-472)
 };
 
 namespace ort {

@@ -522,30 +522,20 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     return ort_scene_create_ex(world, top_most_node, device, flags, scene_out);
 }
 
-int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, uint32_t flags, OrtScene **scene_out)
+// everything after the records are known: build the tree (host or device), upload, create the handle
+static int create_scene_from_records(std::vector<HostPrim> &prims, FlatScene &flat, int device, uint32_t flags,
+                                     OrtBuildStats bs, OrtScene **scene_out)
 {
-    if(!scene_out) return fail(ORT_ERR_ARG, "scene_out is null");
-    *scene_out = 0;
-    int n = 0;
-    if(ort_device_count(&n) != ORT_OK) return ORT_ERR_CUDA;
-    if(device < 0 || device >= n) return fail(ORT_ERR_ARG, "device ordinal out of range");
-    CUDA_TRY(cudaSetDevice(device));
-
-    FlatScene flat;
     std::string err;
+    int rc = ORT_OK;
     BuildOptions opt;
     if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_MERGE_SHAPES")) opt.merge_shapes = atoi(e) != 0;
     const bool on_device = (flags & ORT_BUILD_ON_DEVICE) != 0u;
-    OrtBuildStats bs; memset(&bs, 0, sizeof(bs));
     bs.on_device = on_device ? 1u : 0u;
     build::DeviceBuildResult built; memset(&built, 0, sizeof(built));
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<HostPrim> prims;
-    int rc = collect_records(world, top_most_node, &prims, &flat, &err);
-    if(rc != ORT_OK) return fail(rc, err);
-    bs.collect_s = (float)seconds_since(t0);
     t0 = std::chrono::steady_clock::now();
     if(on_device)
     {
@@ -621,6 +611,47 @@ int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_
     s->info.device_bytes = total;
     *scene_out = s;
     return ORT_OK;
+}
+
+static int check_device(int device, OrtScene **scene_out)
+{
+    if(!scene_out) return fail(ORT_ERR_ARG, "scene_out is null");
+    *scene_out = 0;
+    int n = 0;
+    if(ort_device_count(&n) != ORT_OK) return ORT_ERR_CUDA;
+    if(device < 0 || device >= n) return fail(ORT_ERR_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    return ORT_OK;
+}
+
+int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, uint32_t flags, OrtScene **scene_out)
+{
+    int rc = check_device(device, scene_out);
+    if(rc != ORT_OK) return rc;
+    FlatScene flat;
+    std::string err;
+    OrtBuildStats bs; memset(&bs, 0, sizeof(bs));
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<HostPrim> prims;
+    rc = collect_records(world, top_most_node, &prims, &flat, &err);
+    if(rc != ORT_OK) return fail(rc, err);
+    bs.collect_s = (float)seconds_since(t0);
+    return create_scene_from_records(prims, flat, device, flags, bs, scene_out);
+}
+
+int ort_scene_create_from_lists(const OrtWorld *world, const OrtShapeLists *lists, int device, uint32_t flags, OrtScene **scene_out)
+{
+    int rc = check_device(device, scene_out);
+    if(rc != ORT_OK) return rc;
+    FlatScene flat;
+    std::string err;
+    OrtBuildStats bs; memset(&bs, 0, sizeof(bs));
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<HostPrim> prims;
+    rc = collect_records_from_lists(world, lists, &prims, &flat, &err);
+    if(rc != ORT_OK) return fail(rc, err);
+    bs.collect_s = (float)seconds_since(t0);
+    return create_scene_from_records(prims, flat, device, flags, bs, scene_out);
 }
 
 int ort_scene_build_stats(const OrtScene *s, OrtBuildStats *out)

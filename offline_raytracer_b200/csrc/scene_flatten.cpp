@@ -109,6 +109,46 @@ static void material_constants(DevMaterial *dm)
     dm->lobes = (length_square(Kd) > 0.0f ? 1u : 0u) | (length_square(Ks) > 0.0f ? 2u : 0u) | (length_square(Kt) > 0.0f ? 4u : 0u);
 }
 
+// world-level tables of the flattened scene: materials and the light list
+static int fill_world_tables(const OrtWorld *world, FlatScene *out, std::string *err)
+{
+    // materials (index 0 = "miss", parser.cpp:1187)
+    out->materials.resize(world->mat_count ? world->mat_count : 1);
+    memset(out->materials.data(), 0, out->materials.size() * sizeof(DevMaterial));
+    for(uint32_t i = 0; i < world->mat_count; ++i)
+    {
+        const OrtMaterial &m = world->materials[i];
+        DevMaterial &dm = out->materials[i];
+        dm.diffuse[0] = m.diffuse.x; dm.diffuse[1] = m.diffuse.y; dm.diffuse[2] = m.diffuse.z;
+        dm.specular[0] = m.specular.x; dm.specular[1] = m.specular.y; dm.specular[2] = m.specular.z;
+        dm.transmission[0] = m.transmission.x; dm.transmission[1] = m.transmission.y; dm.transmission[2] = m.transmission.z;
+        dm.emit[0] = m.emit_color.x; dm.emit[1] = m.emit_color.y; dm.emit[2] = m.emit_color.z;
+        dm.ior = m.ior;
+        dm.is_light = m.is_light;
+        material_constants(&dm);
+    }
+    out->info.material_count = world->mat_count;
+
+    // light list: packed (u32 ShapeType, pointer) pairs (push_light, parser.cpp:1144-1182).
+    // Only "is this entry a sphere" matters: it decides how many RNG steps
+    // sample_random_lights consumes (ray.cpp:542, 562).
+    out->light_is_sphere.clear();
+    const uint8_t *lb = (const uint8_t *)world->light_push_buffer.base;
+    const size_t stride = 4 + sizeof(void *);
+    for(size_t consumed = 0; lb && consumed + stride <= world->light_push_buffer.used; consumed += stride)
+    {
+        uint32_t type; memcpy(&type, lb + consumed, 4);
+        out->light_is_sphere.push_back(type == ORT_SHAPE_SPHERE ? 1 : 0);
+    }
+    if(out->light_is_sphere.size() != world->light_count)
+    {
+        *err = "light push buffer does not hold light_count entries";
+        return ORT_ERR_ARG;
+    }
+    out->info.light_count = world->light_count;
+    return ORT_OK;
+}
+
 int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
                     std::vector<HostPrim> *prims, FlatScene *out, std::string *err)
 {
@@ -199,41 +239,7 @@ int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
     out->info.root_min[0] = root->aabb_min.x; out->info.root_min[1] = root->aabb_min.y; out->info.root_min[2] = root->aabb_min.z;
     out->info.root_max[0] = root->aabb_max.x; out->info.root_max[1] = root->aabb_max.y; out->info.root_max[2] = root->aabb_max.z;
 
-    // materials (index 0 = "miss", parser.cpp:1187)
-    out->materials.resize(world->mat_count ? world->mat_count : 1);
-    memset(out->materials.data(), 0, out->materials.size() * sizeof(DevMaterial));
-    for(uint32_t i = 0; i < world->mat_count; ++i)
-    {
-        const OrtMaterial &m = world->materials[i];
-        DevMaterial &dm = out->materials[i];
-        dm.diffuse[0] = m.diffuse.x; dm.diffuse[1] = m.diffuse.y; dm.diffuse[2] = m.diffuse.z;
-        dm.specular[0] = m.specular.x; dm.specular[1] = m.specular.y; dm.specular[2] = m.specular.z;
-        dm.transmission[0] = m.transmission.x; dm.transmission[1] = m.transmission.y; dm.transmission[2] = m.transmission.z;
-        dm.emit[0] = m.emit_color.x; dm.emit[1] = m.emit_color.y; dm.emit[2] = m.emit_color.z;
-        dm.ior = m.ior;
-        dm.is_light = m.is_light;
-        material_constants(&dm);
-    }
-    out->info.material_count = world->mat_count;
-
-    // light list: packed (u32 ShapeType, pointer) pairs (push_light, parser.cpp:1144-1182).
-    // Only "is this entry a sphere" matters: it decides how many RNG steps
-    // sample_random_lights consumes (ray.cpp:542, 562).
-    out->light_is_sphere.clear();
-    const uint8_t *lb = (const uint8_t *)world->light_push_buffer.base;
-    const size_t stride = 4 + sizeof(void *);
-    for(size_t consumed = 0; lb && consumed + stride <= world->light_push_buffer.used; consumed += stride)
-    {
-        uint32_t type; memcpy(&type, lb + consumed, 4);
-        out->light_is_sphere.push_back(type == ORT_SHAPE_SPHERE ? 1 : 0);
-    }
-    if(out->light_is_sphere.size() != world->light_count)
-    {
-        *err = "light push buffer does not hold light_count entries";
-        return ORT_ERR_ARG;
-    }
-    out->info.light_count = world->light_count;
-    return ORT_OK;
+    return fill_world_tables(world, out, err);
 }
 
 // ---------------------------------------------------------------------------
@@ -626,6 +632,214 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
 }
 
 } // namespace
+
+// ---- records and ranks without the octree ---------------------------------------------------------------
+namespace {
+
+inline f3 gmin(f3 a, f3 b) { return mk3(ref_min(a.x, b.x), ref_min(a.y, b.y), ref_min(a.z, b.z)); }   // math.h:1085
+inline f3 gmax(f3 a, f3 b) { return mk3(ref_max(a.x, b.x), ref_max(a.y, b.y), ref_max(a.z, b.z)); }   // math.h:1097
+
+// centre of get_shape_aabb (ray.cpp:1675-1746): the point push_shape_inside_node sorts into octants
+inline f3 box_centre(f3 mn, f3 mx) { return 0.5f * (mn + mx); }
+inline f3 centre_of_cylinder(const OrtCylinder &c)
+{
+    f3 base = v3(c.base), axis = v3(c.axis);
+    f3 other = base + axis;
+    f3 q = hadamard(axis, axis) / dot(axis, axis);
+    f3 e = c.r * (mk3(1, 1, 1) - mk3(sqrtf(q.x), sqrtf(q.y), sqrtf(q.z)));
+    return box_centre(gmin(base - e, other - e), gmax(base + e, other + e));
+}
+
+// the ten octant digits of a shape centre, first level in the top 3 bits of 30
+// (get_bvh_octree_node_child_info, ray.cpp:1476-1522: bit0 = +x, bit1 = +y, bit2 = +z; the child's
+// centre is the parent's -+ half of the parent's half dimension, in float)
+inline uint32_t octant_path(f3 c, f3 node_center, f3 node_half)
+{
+    uint32_t code = 0;
+    for(int level = 0; level < 10; ++level)
+    {
+        f3 h = 0.5f * node_half;
+        uint32_t idx = 0;
+        if(c.x >= node_center.x) { idx |= 1u; node_center.x += h.x; } else node_center.x -= h.x;
+        if(c.y >= node_center.y) { idx |= 2u; node_center.y += h.y; } else node_center.y -= h.y;
+        if(c.z >= node_center.z) { idx |= 4u; node_center.z += h.z; } else node_center.z -= h.z;
+        node_half = h;
+        code = (code << 3) | idx;
+    }
+    return code;
+}
+
+// stable LSD radix sort of (key, payload) pairs on the low `bits` bits of the key
+void radix_sort_pairs(std::vector<uint64_t> &key, std::vector<uint32_t> &val, int bits)
+{
+    size_t n = key.size();
+    std::vector<uint64_t> k2(n); std::vector<uint32_t> v2(n);
+    for(int shift = 0; shift < bits; shift += 11)
+    {
+        size_t count[2049]; memset(count, 0, sizeof(count));
+        for(size_t i = 0; i < n; ++i) count[((key[i] >> shift) & 2047u) + 1]++;
+        for(int b = 0; b < 2048; ++b) count[b + 1] += count[b];
+        for(size_t i = 0; i < n; ++i)
+        {
+            size_t d = count[(key[i] >> shift) & 2047u]++;
+            k2[d] = key[i]; v2[d] = val[i];
+        }
+        key.swap(k2); val.swap(v2);
+    }
+}
+
+inline int common_levels(uint32_t a, uint32_t b)      // leading 3-bit digits two 30-bit paths share
+{
+    uint32_t x = a ^ b;
+    if(x == 0) return 10;
+    int top = 31 - __builtin_clz(x);                   // highest differing bit, 0..29
+    return (29 - top) / 3;
+}
+
+} // namespace
+
+int collect_records_from_lists(const OrtWorld *world, const OrtShapeLists *L,
+                               std::vector<HostPrim> *prims, FlatScene *out, std::string *err)
+{
+    if(!world || !L) { *err = "null world / shape lists"; return ORT_ERR_ARG; }
+    memset(&out->info, 0, sizeof(out->info));
+    // insertion order (macos_main.mm:474-538): triangles mesh by mesh, cylinders, boxes, spheres, CSG
+    std::vector<uint64_t> mesh_first(L->mesh_count + 1, 0);
+    for(uint32_t m = 0; m < L->mesh_count; ++m)
+    {
+        const OrtMesh &mesh = L->meshes[m];
+        if(mesh.index_count && (!mesh.vertices || !mesh.indices)) { *err = "mesh without vertices / indices"; return ORT_ERR_ARG; }
+        mesh_first[m + 1] = mesh_first[m] + mesh.index_count / 3u;
+    }
+    const uint64_t n_tri = mesh_first[L->mesh_count];
+    const uint64_t first_cyl = n_tri, first_box = first_cyl + L->cylinder_count, first_sph = first_box + L->box_count;
+    const uint64_t first_csg = first_sph + L->sphere_count, n = first_csg + (L->csg ? 1u : 0u);
+    if(n >= 0x7FFFFFFFull) { *err = "too many records"; return ORT_ERR_LIMIT; }
+
+    const f3 root_min = v3(L->root_min), root_max = v3(L->root_max);
+    const f3 root_center = 0.5f * (root_min + root_max);            // macos_main.mm:470-471
+    const f3 root_half = root_max - root_center;
+
+    // 1. octant path of every record, in insertion order
+    std::vector<uint64_t> key(n);
+    std::vector<uint32_t> who(n);
+    {
+        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for(unsigned t = 0; t < nt; ++t)
+            pool.emplace_back([&, t]()
+            {
+                for(uint32_t m = 0; m < L->mesh_count; ++m)
+                {
+                    const OrtMesh &mesh = L->meshes[m];
+                    uint64_t cnt = mesh.index_count / 3u;
+                    for(uint64_t k = t; k < cnt; k += nt)
+                    {
+                        f3 a = v3(mesh.vertices[mesh.indices[3 * k]]), b = v3(mesh.vertices[mesh.indices[3 * k + 1]]), c = v3(mesh.vertices[mesh.indices[3 * k + 2]]);
+                        uint64_t i = mesh_first[m] + k;
+                        key[i] = octant_path(box_centre(gmin(gmin(a, b), c), gmax(gmax(a, b), c)), root_center, root_half);
+                    }
+                }
+            });
+        for(auto &th : pool) th.join();
+    }
+    for(uint32_t i = 0; i < L->cylinder_count; ++i) key[first_cyl + i] = octant_path(centre_of_cylinder(L->cylinders[i]), root_center, root_half);
+    for(uint32_t i = 0; i < L->box_count; ++i) key[first_box + i] = octant_path(box_centre(v3(L->boxes[i].min), v3(L->boxes[i].max)), root_center, root_half);
+    for(uint32_t i = 0; i < L->sphere_count; ++i) key[first_sph + i] = octant_path(v3(L->spheres[i].center), root_center, root_half);
+    if(L->csg) key[first_csg] = octant_path(box_centre(v3(L->csg->aabb_min), v3(L->csg->aabb_max)), root_center, root_half);
+    for(uint64_t i = 0; i < n; ++i) who[i] = (uint32_t)i;
+
+    // 2. the node of a record is the shortest prefix of its path no other record shares (capped at 10)
+    std::vector<uint64_t> sorted_key(key);
+    std::vector<uint32_t> sorted_who(who);
+    radix_sort_pairs(sorted_key, sorted_who, 30);
+    std::vector<uint8_t> depth(n);
+    uint32_t max_depth = 0;
+    for(uint64_t p = 0; p < n; ++p)
+    {
+        int shared = 0;
+        if(p > 0) shared = std::max(shared, common_levels((uint32_t)sorted_key[p], (uint32_t)sorted_key[p - 1]));
+        if(p + 1 < n) shared = std::max(shared, common_levels((uint32_t)sorted_key[p], (uint32_t)sorted_key[p + 1]));
+        int d = n == 1 ? 0 : std::min(shared + 1, 10);
+        depth[sorted_who[p]] = (uint8_t)d;
+        if((uint32_t)d > max_depth) max_depth = (uint32_t)d;
+    }
+    // octree statistics, as collect_records reports them (nodes reachable through live children):
+    // every prefix shared by two or more records is an inner node; the others hold records
+    uint64_t inner = 0;
+    for(int level = 0; level < 10 && n >= 2; ++level)
+    {
+        int shift = 3 * (10 - level);
+        uint64_t run = 1;
+        for(uint64_t p = 1; p <= n; ++p)
+        {
+            bool same = p < n && (level == 0 || (sorted_key[p] >> shift) == (sorted_key[p - 1] >> shift));
+            if(same) { ++run; continue; }
+            if(run >= 2) ++inner;
+            run = 1;
+        }
+    }
+    std::vector<uint64_t>().swap(sorted_key);
+    std::vector<uint32_t>().swap(sorted_who);
+    // 3. breadth-first node order = (depth, prefix); push-buffer order inside a node = insertion order
+    for(uint64_t i = 0; i < n; ++i)
+    {
+        uint32_t d = depth[i];
+        key[i] = ((uint64_t)d << 30) | (d == 0 ? 0u : (key[i] >> (3 * (10 - d))));
+    }
+    radix_sort_pairs(key, who, 34);
+    uint64_t holding = 0;
+    for(uint64_t p = 0; p < n; ++p) if(p == 0 || key[p] != key[p - 1]) ++holding;
+
+    // 4. records, in rank order (the order collect_records emits them)
+    prims->clear();
+    prims->reserve(n);
+    for(uint64_t rank = 0; rank < n; ++rank)
+    {
+        uint64_t i = who[rank];
+        HostPrim p; memset(&p, 0, sizeof(p));
+        p.rank = (uint32_t)rank;
+        if(i < n_tri)
+        {
+            uint32_t m = (uint32_t)(std::upper_bound(mesh_first.begin(), mesh_first.end(), i) - mesh_first.begin()) - 1u;
+            const OrtMesh &mesh = L->meshes[m];
+            uint64_t k = i - mesh_first[m];
+            uint32_t i0 = mesh.indices[3 * k], i1 = mesh.indices[3 * k + 1], i2 = mesh.indices[3 * k + 2];
+            if(i0 >= mesh.vertex_count || i1 >= mesh.vertex_count || i2 >= mesh.vertex_count) { *err = "mesh index out of range"; return ORT_ERR_ARG; }
+            p.kind = PRIM_TRIANGLE; p.a = v3(mesh.vertices[i0]); p.b = v3(mesh.vertices[i1]); p.c = v3(mesh.vertices[i2]);
+            p.mat = mesh.mat_index;
+            out->info.triangle_count++;
+        }
+        else if(i < first_box)
+        {
+            const OrtCylinder &s = L->cylinders[i - first_cyl];
+            p.kind = PRIM_CYLINDER; p.a = v3(s.base); p.b = v3(s.axis); p.radius = s.r; p.mat = s.mat_index;
+            out->info.cylinder_count++;
+        }
+        else if(i < first_sph)
+        {
+            const OrtAAB &s = L->boxes[i - first_box];
+            p.kind = PRIM_AAB; p.a = v3(s.min); p.b = v3(s.max); p.mat = s.mat_index;
+            out->info.box_count++;
+        }
+        else if(i < first_csg)
+        {
+            const OrtSphere &s = L->spheres[i - first_sph];
+            p.kind = PRIM_SPHERE; p.a = v3(s.center); p.radius = s.r; p.mat = s.mat_index;
+            out->info.sphere_count++;
+        }
+        else { out->info.csg_count++; continue; }       // inert record, ray.cpp:718-767: a rank, nothing to test
+        if(p.mat >= world->mat_count) { *err = "record with material index out of range"; return ORT_ERR_ARG; }
+        prim_bounds(p);
+        prims->push_back(p);
+    }
+    out->info.record_count = (uint32_t)n;
+    out->info.octree_node_count = (uint32_t)(inner + holding);
+    out->info.octree_max_depth = max_depth;
+    out->info.root_min[0] = L->root_min.x; out->info.root_min[1] = L->root_min.y; out->info.root_min[2] = L->root_min.z;
+    out->info.root_max[0] = L->root_max.x; out->info.root_max[1] = L->root_max.y; out->info.root_max[2] = L->root_max.z;
+    return fill_world_tables(world, out, err);
+}
 
 // pads the primitive boxes (see bvh.h: conservative culling) and separates the spheres, which get
 // a tree of their own, from the rest

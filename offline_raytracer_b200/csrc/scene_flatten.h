@@ -67,6 +67,9 @@ struct FlatScene
 // decode the octree into ranked records (+ world materials / light list)
 int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
                     std::vector<HostPrim> *prims, FlatScene *out, std::string *err);
+// the same records and ranks from the shape lists alone, no octree (include/ort_b200.h, OrtShapeLists)
+int collect_records_from_lists(const OrtWorld *world, const OrtShapeLists *lists,
+                               std::vector<HostPrim> *prims, FlatScene *out, std::string *err);
 // build the wide BVH over `prims` (consumed) into out->nodes / prims / cylinders
 int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, std::string *err);
 

@@ -63,6 +63,29 @@ void *sim_scene_create_parallel(const OrtWorld *world, const OrtBVHOctreeNode *r
     s->view.tri_root = s->flat.tri_root;
     return s;
 }
+// records + ranks WITHOUT the octree (collect_records_from_lists), then the usual host SAH build
+void *sim_scene_create_from_lists(const OrtWorld *world, const OrtShapeLists *lists)
+{
+    SimScene *s = new SimScene();
+    BuildOptions opt;
+    std::string err;
+    std::vector<HostPrim> prims;
+    int rc = collect_records_from_lists(world, lists, &prims, &s->flat, &err);
+    if(rc == ORT_OK) rc = build_wide_bvh(prims, opt, &s->flat, &err);
+    if(rc != ORT_OK)
+    {
+        fprintf(stderr, "sim_scene_create_from_lists: %s\n", err.c_str());
+        delete s; return 0;
+    }
+    s->view.nodes = (const q4 *)s->flat.nodes.data();
+    s->view.prims = (const q4 *)s->flat.prims.data();
+    s->view.cyl = (const q4 *)s->flat.cylinders.data();
+    s->view.node_count = (uint32_t)s->flat.nodes.size();
+    s->view.prim_count = (uint32_t)s->flat.prims.size();
+    s->view.main_root = s->flat.main_root;
+    s->view.tri_root = s->flat.tri_root;
+    return s;
+}
 // raw bytes of the flattened tree, for byte-for-byte comparison with the CUDA execution
 uint64_t sim_scene_nodes(void *h, const void **p) { SimScene *s = (SimScene *)h; *p = s->flat.nodes.data(); return s->flat.nodes.size() * sizeof(WideNode); }
 uint64_t sim_scene_prims(void *h, const void **p) { SimScene *s = (SimScene *)h; *p = s->flat.prims.data(); return s->flat.prims.size() * sizeof(PrimRec); }

@@ -211,3 +211,49 @@ def test_parallel_builder_gives_the_same_hits_with_comparable_work(sim, testscen
     recs_sah = np.frombuffer((C.c_char * na).from_address(p.value), np.uint32).reshape(-1, 12)
     assert nb == na and np.array_equal(np.sort(recs[:, 3]), np.sort(recs_sah[:, 3]))
     L.sim_scene_destroy(h_par); L.sim_scene_destroy(h_sah)
+
+
+@pytest.mark.parametrize("scene", ["testscene", "box_spheres", "c3_bunny_box", "c4_dwarf_hdr"])
+def test_ranks_from_shape_lists_equal_ranks_from_the_octree(sim, ort, scene):
+    """the tie-break ranks -- breadth-first octree order, push-buffer order within a node --
+    computed from the shape lists alone by two radix sorts (collect_records_from_lists) equal those read
+    off the octree that push_shape_inside_node builds (ray.cpp:1799-1948), record for record; so do the
+    octree statistics and, therefore, the whole flattened scene."""
+    base = ol.DATA_DIR
+    path = os.path.join(ol.DATA_DIR, "testscene.scn") if scene == "testscene" else os.path.join(ol.SCENES_DIR, scene + ".scn")
+    if scene == "box_spheres":
+        base = ol.SCENES_DIR
+    hs = ort.HostScene.load(path, base, 64, 36)
+    L = sim.L
+    L.sim_scene_create_from_lists.restype = vp
+    L.sim_scene_create_from_lists.argtypes = [vp, vp]
+    L.sim_scene_nodes.restype = C.c_uint64; L.sim_scene_nodes.argtypes = [vp, C.POINTER(vp)]
+    L.sim_scene_prims.restype = C.c_uint64; L.sim_scene_prims.argtypes = [vp, C.POINTER(vp)]
+    L.sim_scene_info.argtypes = [vp, vp, vp]
+    lists = hs.lists()
+    a = sim.scene(hs.world, hs.root)
+    b = L.sim_scene_create_from_lists(hs.world, C.byref(lists))
+    assert b
+
+    def dump(h):
+        p = vp()
+        nb = L.sim_scene_nodes(h, C.byref(p))
+        nodes = np.frombuffer((C.c_char * nb).from_address(p.value), np.uint8).copy()
+        nb = L.sim_scene_prims(h, C.byref(p))
+        prims = np.frombuffer((C.c_char * nb).from_address(p.value), np.uint32).reshape(-1, 12).copy()
+        info = ort.api.SceneInfo(); depth = C.c_uint32(0)
+        L.sim_scene_info(h, C.byref(info), C.byref(depth))
+        return nodes, prims, info.as_dict()
+
+    na, pa, ia = dump(a)
+    nb_, pb, ib = dump(b)
+    assert ia == ib, (ia, ib)
+    assert np.array_equal(pa, pb) and np.array_equal(na, nb_)
+    # without the octree at all
+    hs2 = ort.HostScene.load(path, base, 64, 36, octree=False)
+    assert not hs2.root
+    c = L.sim_scene_create_from_lists(hs2.world, C.byref(hs2.lists()))
+    nc, pc, ic = dump(c)
+    assert ic == ia and np.array_equal(pc, pa)
+    for h in (a, b, c):
+        L.sim_scene_destroy(h)
