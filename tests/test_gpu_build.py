@@ -78,3 +78,23 @@ def test_device_built_scene_gives_identical_hits_and_images(ort, testscene_host,
     ib, _ = b.render(hs.camera, P)
     assert np.array_equal(bits(ia), bits(ib))
     a.close(); b.close()
+
+
+def test_scene_from_shape_lists_on_the_device(ort, testscene_host, tmp_path):
+    """no octree anywhere: lists -> ranks by sorting -> device build; same hits, same image"""
+    hs = testscene_host
+    a = ort.Scene(hs.world, hs.root, 0, build_on_device=False)
+    hs2 = ort.HostScene.load(os.path.join(ol.DATA_DIR, "testscene.scn"), ol.DATA_DIR, hs.width, hs.height, octree=False)
+    b = ort.Scene.from_lists(hs2.world, hs2.lists(), 0, build_on_device=True)
+    ia, ib = a.info(), b.info()
+    for k in ("triangle_count", "record_count", "octree_node_count", "octree_max_depth", "root_min", "root_max"):
+        assert ia[k] == ib[k], k
+    o, d = ol.make_incoherent_rays(300000, [-2.9, -2.9, 0.0], [14.9, 14.9, 8.8])
+    ra, rb = a.raycast_batch(o, d), b.raycast_batch(o, d)
+    assert np.array_equal(ra["rank"], rb["rank"]) and np.array_equal(bits(ra["t"]), bits(rb["t"]))
+    assert np.array_equal(ra["mat"], rb["mat"]) and np.array_equal(bits(ra["normal"]), bits(rb["normal"]))
+    P = ort.default_params(160, 90, 4, chunk_spp=2, kernel=ort.ORT_KERNEL_WAVEFRONT)
+    ia_, _ = a.render(hs.camera, P)
+    ib_, _ = b.render(hs2.camera, P)
+    assert np.array_equal(bits(ia_), bits(ib_))
+    a.close(); b.close()

@@ -259,7 +259,7 @@ def test_more_than_255_materials(ort, tmp_path):
         c = rng.uniform(0.2, 0.9, 3)
         x, y = -2.8 + 0.28 * (i % 20), -1.9 + 0.25 * (i // 20)
         lines += ["brdf %.3f %.3f %.3f 0.0 0.0 0.0 10 0.0 0.0 0.0 1.0" % tuple(c), "box %.3f %.3f -2.5 0.2 0.2 0.2" % (x, y)]
-    lines += ["light 6.0 6.0 6.0", "sphere 0.0 1.4 1.0 0.4", ""]
+    lines += ["light 6 6 6", "sphere 0.0 1.4 1.0 0.4", ""]
     path = tmp_path / "many_materials.scn"
     path.write_text("\n".join(lines))
     W2, H2, SPP = 160, 90, 8

@@ -18,13 +18,17 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--kernel", type=int, default=0)
 ap.add_argument("--lib", default="")
 ap.add_argument("--build", default="", help="host | device (default: ort_scene_create's choice)")
+ap.add_argument("--lists", action="store_true", help="hand the scene over as shape lists, without building the octree")
 a = ap.parse_args()
 import time
 t0 = time.time()
-hs = ort.HostScene.load(a.scene, a.base, a.width, a.height)
+hs = ort.HostScene.load(a.scene, a.base, a.width, a.height, octree=not a.lists)
 t1 = time.time()
-sc = ort.Scene(hs.world, hs.root, 0, library=ort.lib(os.path.abspath(a.lib)) if a.lib else None,
-               build_on_device={"": None, "host": False, "device": True}[a.build])
+if a.lists:
+    sc = ort.Scene.from_lists(hs.world, hs.lists(), 0, build_on_device=a.build == "device")
+else:
+    sc = ort.Scene(hs.world, hs.root, 0, library=ort.lib(os.path.abspath(a.lib)) if a.lib else None,
+                   build_on_device={"": None, "host": False, "device": True}[a.build])
 t2 = time.time()
 inf, bs = sc.info(), sc.build_stats()
 print("load %.2f s | scene_create %.2f s: collect %.2f prepare %.2f build %.2f (device kernels %.1f ms, %d PLOC rounds) | "
