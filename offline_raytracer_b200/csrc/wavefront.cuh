@@ -26,8 +26,8 @@
 //   q1  direction.xyz | 1 if the ray is a primary            }
 //   q2  wo.xyz | xorshift state of the stream
 //   q3  throughput weight.xyz | pixel index
-//   q4  radiance sum of the stream so far .xyz | samples left (bit 31: ray is a primary)
-//   q5  hit t | hit primitive | chunk index of the stream | -      EXTEND writes .xy
+//   q4  radiance sum of the stream so far .xyz | samples left        } written only when a path ends
+//   q5  hit t | hit primitive | chunk index of the stream | -        } EXTEND writes .xy
 // plus key[] (shading key per slot) and perm[] (slots in key order), 4 B each, coalesced.
 #pragma once
 
@@ -734,9 +734,8 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
             p.weight = mk3(sw.x, sw.y, sw.z);
             const uint32_t pixel_index = __float_as_uint(sw.w);
             f3 color = mk3(scol.x, scol.y, scol.z);
-            uint32_t sl = __float_as_uint(scol.w);
-            const bool primary = (sl >> 31) != 0u;
-            const uint32_t samples_left = sl & 0x7FFFFFFFu;
+            const bool primary = __float_as_uint(rd.w) != 0u;
+            const uint32_t samples_left = __float_as_uint(scol.w);
             p.normal = mk3(0.f, 0.f, 0.f); p.mat = 0u;
             uint32_t mat; f3 nrm;
             wf_finish_hit(a.scene, h.y, p.origin, p.dir, &mat, &nrm);
@@ -749,8 +748,8 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
                 rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(0u));
                 rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
                 rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
-                rec[4] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left));
-                rec[5] = make_float4(0.f, 0.f, __uint_as_float(chunk), 0.f);
+                // q4 (radiance sum, samples left) and q5 (chunk) do not change while a path continues --
+                // only a path that ends adds to the sum -- so their sector is not written back
                 still_active = 1;
             }
             else
@@ -845,7 +844,7 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
             rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(1u));
             rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
             rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
-            rec[4] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left | 0x80000000u));
+            rec[4] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left));
             rec[5] = make_float4(0.f, 0.f, __uint_as_float(chunk), 0.f);
             still_active += 1;
         }
