@@ -130,7 +130,7 @@ int check_params(const OrtRenderParams *P)
 {
     if(!P) return fail(ORT_ERR_ARG, "null params");
     if(P->output_width <= 0 || P->output_height <= 0) return fail(ORT_ERR_ARG, "output size must be positive");
-    if((int64_t)P->output_width * P->output_height > 0x7FFFFFFFll) return fail(ORT_ERR_ARG, "image too large");
+    if((int64_t)P->output_width * P->output_height >= (int64_t)WF_PIXEL_MASK) return fail(ORT_ERR_ARG, "image too large (2^29 - 1 pixels at most)");
     if(P->tile_min_x < 0 || P->tile_min_y < 0 || P->tile_one_past_max_x > P->output_width ||
        P->tile_one_past_max_y > P->output_height || P->tile_min_x > P->tile_one_past_max_x ||
        P->tile_min_y > P->tile_one_past_max_y)

@@ -21,13 +21,18 @@
 // Slot state: one 96-byte record per slot = 6 x 16 B = exactly three 32-byte sectors, so the
 // SHADE stage -- which visits slots in material order, i.e. at random addresses -- moves only
 // bytes it uses (a structure-of-arrays layout fetched a 32-byte sector for every 16 bytes and
-// made SHADE HBM-bound: its time fell 23 % just by shrinking the pool into L2).
-//   q0  origin.xyz | state (DEAD / ACTIVE / FRESH)          } EXTEND reads q0,q1: one sector
-//   q1  direction.xyz | 1 if the ray is a primary            }
-//   q2  wo.xyz | xorshift state of the stream
-//   q3  throughput weight.xyz | pixel index
-//   q4  radiance sum of the stream so far .xyz | samples left        } written only when a path ends
-//   q5  hit t | hit primitive | chunk index of the stream | -        } EXTEND writes .xy
+// made SHADE HBM-bound: its time fell 23 % just by shrinking the pool into L2).  The fields are
+// grouped by who touches them, because after the instruction diet of SHADE the stage moves
+// ~3 TB/s of these records:
+//   sector 0   q0  origin.xyz | hit t                          EXTEND reads it and writes t, prim
+//              q1  direction.xyz | flags, then hit primitive   back into the SAME sector (no fill)
+//   sector 1   q2  wo.xyz | xorshift state of the stream
+//              q3  throughput weight.xyz | pixel index (29 bits) + state (2 bits) + primary (1 bit)
+//   sector 2   q4  radiance sum of the stream so far .xyz | samples left     read and written only
+//              q5  chunk index of the stream | - | - | -                     when a path ENDS
+// A continuing path (4 of 5) therefore costs SHADE two sectors in and two out, not three.
+// q1.w carries the flags (state, primary) from SHADE to EXTEND, which overwrites it with the hit
+// primitive; q3.w keeps them for SHADE.
 // plus key[] (shading key per slot) and perm[] (slots in key order), 4 B each, coalesced.
 #pragma once
 
@@ -36,6 +41,9 @@
 namespace ort {
 
 enum { WF_DEAD = 0u, WF_ACTIVE = 1u, WF_FRESH = 2u };
+#define WF_PIXEL_MASK 0x1FFFFFFFu           // also "no pixel yet"
+__device__ __forceinline__ uint32_t wf_flags(uint32_t state, bool primary) { return (state << 29) | (primary ? 0x80000000u : 0u); }
+__device__ __forceinline__ uint32_t wf_state_of(uint32_t word) { return (word >> 29) & 3u; }
 
 #define WF_REC_QUADS 6u
 
@@ -50,7 +58,14 @@ struct WfBuffers
 __global__ void k_wf_reset(WfBuffers wf)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < wf.capacity) wf.rec[WF_REC_QUADS * i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_FRESH));
+    if(i < wf.capacity)
+    {
+        float4 *rec = wf.rec + (size_t)WF_REC_QUADS * i;
+        rec[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(wf_flags(WF_FRESH, false)));
+        rec[3] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_PIXEL_MASK | wf_flags(WF_FRESH, false)));
+        rec[4] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        rec[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // shared-memory traversal stack: entry k of thread t lives at column t of row k, so the 32
@@ -63,14 +78,16 @@ struct SharedStack
     __device__ __forceinline__ void get(int i, uint32_t &a, uint32_t &b) const { uint2 v = col[i * 128]; a = v.x; b = v.y; }
 };
 
-// EXTEND's result: q5.xy = (t, primitive)
+// EXTEND's result goes back into the sector the ray came from: q0.w = t, q1.w = primitive
 // (tried, B200: also storing the material here and loading the whole record + material up front in
 //  SHADE, to shorten its chain of dependent loads -- SHADE 133.1 vs 130.7 ms, the extra live registers
 //  cost more than the shorter chain saves)
 __device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot, float t, uint32_t prim, uint32_t mat)
 {
     (void)mat;
-    *reinterpret_cast<uint2 *>(wf.rec + WF_REC_QUADS * slot + 5u) = make_uint2(__float_as_uint(t), prim);
+    float *r = reinterpret_cast<float *>(wf.rec + (size_t)WF_REC_QUADS * slot);
+    r[3] = t;
+    r[7] = __uint_as_float(prim);
 }
 
 #define WF_KEY_DEAD 511u
@@ -139,12 +156,11 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
             uint32_t my = next + __popc(idle_mask & ((1u << lane) - 1u));
             if(!has_ray && my < end)
             {
-                float4 ro = wf.rec[WF_REC_QUADS * my];
-                if(__float_as_uint(ro.w) == WF_ACTIVE)
+                float4 ro = wf.rec[WF_REC_QUADS * my], rd = wf.rec[WF_REC_QUADS * my + 1u];      // one sector, one round trip
+                if(wf_state_of(__float_as_uint(rd.w)) == WF_ACTIVE)
                 {
-                    float4 rd = wf.rec[WF_REC_QUADS * my + 1u];
                     trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
-                    is_primary = __float_as_uint(rd.w);
+                    is_primary = __float_as_uint(rd.w) >> 31;
                     slot = my;
                     has_ray = true;
                     ++rays;
@@ -269,12 +285,11 @@ k_wf_extend_v(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned l
             uint32_t my = next + __popc(idle_mask & ((1u << lane) - 1u));
             if(!has_ray && my < end)
             {
-                float4 ro = wf.rec[WF_REC_QUADS * my];
-                if(__float_as_uint(ro.w) == WF_ACTIVE)
+                float4 ro = wf.rec[WF_REC_QUADS * my], rd = wf.rec[WF_REC_QUADS * my + 1u];      // one sector, one round trip
+                if(wf_state_of(__float_as_uint(rd.w)) == WF_ACTIVE)
                 {
-                    float4 rd = wf.rec[WF_REC_QUADS * my + 1u];
                     trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
-                    is_primary = __float_as_uint(rd.w);
+                    is_primary = __float_as_uint(rd.w) >> 31;
                     slot = my;
                     has_ray = true;
                     pg_y = 0u;
@@ -454,12 +469,11 @@ k_wf_extend_q(SceneView scene, WfBuffers wf, const uint32_t *__restrict__ rank_t
                 uint32_t my = next + __popc(free_mask & lt_mask);
                 if(!has_ray && my < end)
                 {
-                    float4 ro = wf.rec[WF_REC_QUADS * my];
-                    if(__float_as_uint(ro.w) == WF_ACTIVE)
+                    float4 ro = wf.rec[WF_REC_QUADS * my], rd = wf.rec[WF_REC_QUADS * my + 1u];      // one sector, one round trip
+                    if(wf_state_of(__float_as_uint(rd.w)) == WF_ACTIVE)
                     {
-                        float4 rd = wf.rec[WF_REC_QUADS * my + 1u];
                         trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
-                        is_primary = __float_as_uint(rd.w);
+                        is_primary = __float_as_uint(rd.w) >> 31;
                         slot = my;
                         has_ray = true; node_active = true;
                         *my_best = 0x7F7FFFFFFFFFFFFFull;          // (FLT_MAX, MISS)
@@ -690,10 +704,10 @@ __device__ __forceinline__ void wf_finish_hit(const SceneView &s, uint32_t prim,
 // full warps, ACCUMULATE the finished stream, pull the next one and GENERATE the camera ray.  (ncu:
 // done in place by the thread that owned the slot, these ~300 instructions ran with 6.8 of 32 lanes
 // and every warp paid for them.)
-struct WfRegen           // what phase 2 needs to know about a slot, 32 B
+struct WfRegen           // what phase 2 needs to know about a slot whose path ended, 32 B
 {
-    float cx, cy, cz;            // radiance sum of the stream so far
-    uint32_t series, pixel_index, samples_left, chunk, slot;
+    float dx, dy, dz;            // radiance the path adds to its stream's sum
+    uint32_t series, pixel_index, slot, pad0, pad1;
 };
 
 __global__ void __launch_bounds__(128, ORT_SHADE_MIN_BLOCKS)
@@ -717,49 +731,47 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
     // ---- phase 1: shade + next bounce ----
     bool regen = false;
     WfRegen rg;
-    rg.cx = rg.cy = rg.cz = 0.f; rg.series = 0u; rg.pixel_index = 0xFFFFFFFFu; rg.samples_left = 0u; rg.chunk = 0u; rg.slot = i;
+    rg.dx = rg.dy = rg.dz = 0.f; rg.series = 0u; rg.pixel_index = WF_PIXEL_MASK; rg.slot = i; rg.pad0 = rg.pad1 = 0u;
     if(in_range)
     {
         float4 *rec = wf.rec + (size_t)WF_REC_QUADS * i;
-        float4 ro = rec[0];
-        uint32_t state = __float_as_uint(ro.w);
+        float4 ro = rec[0], rd = rec[1], swo = rec[2], sw = rec[3];
+        const uint32_t word = __float_as_uint(sw.w);
+        const uint32_t state = wf_state_of(word);
         if(state == WF_ACTIVE)
         {
             Path p;
-            float4 rd = rec[1], swo = rec[2], sw = rec[3], scol = rec[4], hq = rec[5];
-            uint2 h = make_uint2(__float_as_uint(hq.x), __float_as_uint(hq.y));
-            const uint32_t chunk = __float_as_uint(hq.z);
             p.origin = mk3(ro.x, ro.y, ro.z); p.dir = mk3(rd.x, rd.y, rd.z);
             p.wo = mk3(swo.x, swo.y, swo.z); p.series = __float_as_uint(swo.w);
             p.weight = mk3(sw.x, sw.y, sw.z);
-            const uint32_t pixel_index = __float_as_uint(sw.w);
-            f3 color = mk3(scol.x, scol.y, scol.z);
-            const bool primary = __float_as_uint(rd.w) != 0u;
-            const uint32_t samples_left = __float_as_uint(scol.w);
+            const uint32_t pixel_index = word & WF_PIXEL_MASK;
+            const bool primary = (word >> 31) != 0u;
+            const float hit_t = ro.w;
+            const uint32_t hit_prim = __float_as_uint(rd.w);
+            // what this hit adds to the stream's radiance sum: `sum = sum + delta` below is the very
+            // addition ray.cpp:1257 / 1364 perform (a path adds at most once, when it ends on a light)
+            f3 delta = mk3(0.f, 0.f, 0.f);
             p.normal = mk3(0.f, 0.f, 0.f); p.mat = 0u;
             uint32_t mat; f3 nrm;
-            wf_finish_hit(a.scene, h.y, p.origin, p.dir, &mat, &nrm);
-            float hit_t = __uint_as_float(h.x);
-            bool alive = primary ? shade_primary(a.pc, &p, hit_t, mat, nrm, &color)
-                                 : shade_bounce(a.pc, &p, hit_t, mat, nrm, &color);
+            wf_finish_hit(a.scene, hit_prim, p.origin, p.dir, &mat, &nrm);
+            bool alive = primary ? shade_primary(a.pc, &p, hit_t, mat, nrm, &delta)
+                                 : shade_bounce(a.pc, &p, hit_t, mat, nrm, &delta);
             if(alive && next_bounce(a.pc, &p))
             {
-                rec[0] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
-                rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(0u));
+                rec[0] = make_float4(p.origin.x, p.origin.y, p.origin.z, 0.f);
+                rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(wf_flags(WF_ACTIVE, false)));
                 rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
-                rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
-                // q4 (radiance sum, samples left) and q5 (chunk) do not change while a path continues --
-                // only a path that ends adds to the sum -- so their sector is not written back
+                rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index | wf_flags(WF_ACTIVE, false)));
                 still_active = 1;
             }
             else
             {
                 regen = true;
-                rg.cx = color.x; rg.cy = color.y; rg.cz = color.z;
-                rg.series = p.series; rg.pixel_index = pixel_index; rg.samples_left = samples_left; rg.chunk = chunk;
+                rg.dx = delta.x; rg.dy = delta.y; rg.dz = delta.z;
+                rg.series = p.series; rg.pixel_index = pixel_index;
             }
         }
-        else if(state == WF_FRESH) regen = true;      // no stream yet: samples_left 0, no pixel
+        else if(state == WF_FRESH) regen = true;      // no stream yet: samples left 0, no pixel
     }
     // ---- compaction of the slots to regenerate ----
     {
@@ -776,15 +788,16 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
     {
         rg = sh_regen[threadIdx.x];
         float4 *rec = wf.rec + (size_t)WF_REC_QUADS * rg.slot;
-        f3 color = mk3(rg.cx, rg.cy, rg.cz);
-        uint32_t samples_left = rg.samples_left, pixel_index = rg.pixel_index, chunk = rg.chunk;
+        float4 scol = rec[4], sch = rec[5];                 // the third sector: only paths that end touch it
+        f3 color = mk3(scol.x, scol.y, scol.z) + mk3(rg.dx, rg.dy, rg.dz);
+        uint32_t samples_left = __float_as_uint(scol.w), pixel_index = rg.pixel_index, chunk = __float_as_uint(sch.x);
         Path p;
         p.series = rg.series;
         bool dead = false;
         if(samples_left == 0)
         {
             // ---- accumulate the finished stream (ray.cpp:1428) ----
-            if(pixel_index != 0xFFFFFFFFu)
+            if(pixel_index != WF_PIXEL_MASK)
             {
                 if(a.accum)
                 {
@@ -831,7 +844,8 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
         }
         if(dead)
         {
-            rec[0] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_DEAD));
+            rec[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(wf_flags(WF_DEAD, false)));
+            rec[3] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_PIXEL_MASK | wf_flags(WF_DEAD, false)));
         }
         else
         {
@@ -840,12 +854,12 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
             generate_primary(a.pc, pixel_focal_point(a.pc, x, y), &p);
             --samples_left;
             n_samples = 1;
-            rec[0] = make_float4(p.origin.x, p.origin.y, p.origin.z, __uint_as_float(WF_ACTIVE));
-            rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(1u));
+            rec[0] = make_float4(p.origin.x, p.origin.y, p.origin.z, 0.f);
+            rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(wf_flags(WF_ACTIVE, true)));
             rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
-            rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index));
+            rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index | wf_flags(WF_ACTIVE, true)));
             rec[4] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left));
-            rec[5] = make_float4(0.f, 0.f, __uint_as_float(chunk), 0.f);
+            rec[5] = make_float4(__uint_as_float(chunk), 0.f, 0.f, 0.f);
             still_active += 1;
         }
     }
