@@ -39,6 +39,51 @@ struct Item { uint32_t b2, wide; };      // binary subtree to turn into the wide
 
 struct Kids { uint32_t id[8]; uint32_t nk; uint32_t n_inner, n_prims; };
 
+// ---- 0. records and ranks straight from the shape lists (include/ort_b200.h, OrtShapeLists) ---------
+// the ten octant digits of a shape centre, first level in the top 3 bits of 30
+// (get_bvh_octree_node_child_info, ray.cpp:1476-1522: bit0 = +x, bit1 = +y, bit2 = +z; the child's
+// centre is the parent's -+ half of the parent's half dimension, in float)
+ORT_HD uint32_t octant_path(f3 c, f3 node_center, f3 node_half)
+{
+    uint32_t code = 0;
+    for(int level = 0; level < 10; ++level)
+    {
+        f3 h = 0.5f * node_half;
+        uint32_t idx = 0;
+        if(c.x >= node_center.x) { idx |= 1u; node_center.x += h.x; } else node_center.x -= h.x;
+        if(c.y >= node_center.y) { idx |= 2u; node_center.y += h.y; } else node_center.y -= h.y;
+        if(c.z >= node_center.z) { idx |= 4u; node_center.z += h.z; } else node_center.z -= h.z;
+        node_half = h;
+        code = (code << 3) | idx;
+    }
+    return code;
+}
+ORT_HD int common_levels(uint32_t a, uint32_t b)      // leading 3-bit digits two 30-bit paths share
+{
+    uint32_t x = a ^ b;
+    if(x == 0) return 10;
+    int top = (int)msb32(x);                           // highest differing bit, 0..29
+    return (29 - top) / 3;
+}
+// centre of a triangle's box as get_shape_aabb forms it (ray.cpp:1675-1746)
+ORT_HD f3 triangle_centre(f3 a, f3 b, f3 c)
+{
+    f3 mn = mk3(ref_min(ref_min(a.x, b.x), c.x), ref_min(ref_min(a.y, b.y), c.y), ref_min(ref_min(a.z, b.z), c.z));
+    f3 mx = mk3(ref_max(ref_max(a.x, b.x), c.x), ref_max(ref_max(a.y, b.y), c.y), ref_max(ref_max(a.z, b.z), c.z));
+    return 0.5f * (mn + mx);
+}
+// conservative padding of a primitive box (bvh.h): relative to its own diagonal plus an absolute term
+ORT_HD void pad_box(float *lo, float *hi, double pad_rel, double pad_abs)
+{
+    double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+    double pad = pad_rel * sqrt(dx * dx + dy * dy + dz * dz) + pad_abs;
+    for(int k = 0; k < 3; ++k)
+    {
+        lo[k] = nextafterf((float)((double)lo[k] - pad), -INFINITY);
+        hi[k] = nextafterf((float)((double)hi[k] + pad), INFINITY);
+    }
+}
+
 // ---- 1. Morton codes ---------------------------------------------------------------------------
 ORT_HD uint64_t spread21(uint64_t v)
 {

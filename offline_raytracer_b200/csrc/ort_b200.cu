@@ -522,6 +522,8 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
     return ort_scene_create_ex(world, top_most_node, device, flags, scene_out);
 }
 
+static int make_scene_handle(FlatScene &flat, build::DeviceBuildResult &built, bool on_device, OrtBuildStats bs, int device, OrtScene **scene_out);
+
 // everything after the records are known: build the tree (host or device), upload, create the handle
 static int create_scene_from_records(std::vector<HostPrim> &prims, FlatScene &flat, int device, uint32_t flags,
                                      OrtBuildStats bs, OrtScene **scene_out)
@@ -569,7 +571,12 @@ static int create_scene_from_records(std::vector<HostPrim> &prims, FlatScene &fl
         bs.build_s = (float)seconds_since(t0);
     }
     bs.wide_depth = flat.wide_depth;
+    return make_scene_handle(flat, built, on_device, bs, device, scene_out);
+}
 
+static int make_scene_handle(FlatScene &flat, build::DeviceBuildResult &built, bool on_device, OrtBuildStats bs, int device, OrtScene **scene_out)
+{
+    int rc = ORT_OK;
     OrtScene *s = new OrtScene();
     memset(s, 0, sizeof(*s));
     s->device = device;
@@ -647,6 +654,41 @@ int ort_scene_create_from_lists(const OrtWorld *world, const OrtShapeLists *list
     std::string err;
     OrtBuildStats bs; memset(&bs, 0, sizeof(bs));
     auto t0 = std::chrono::steady_clock::now();
+    if(flags & ORT_BUILD_ON_DEVICE)
+    {
+        // records, ranks and the tree all on the device: the host touches the meshes only to copy them
+        if(!world || !lists) return fail(ORT_ERR_ARG, "null world / shape lists");
+        BuildOptions opt;
+        if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
+        if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
+        ParallelBuildInput in;
+        build::DeviceRecords dr;
+        if(!build::records_from_lists_on_device(world, lists, opt, &flat, &in, &dr, &err)) return fail(ORT_ERR_CUDA, err);
+        bs.on_device = 1u;
+        bs.collect_s = (float)seconds_since(t0);
+        bs.prepare_s = dr.records_ms * 1e-3f;
+        t0 = std::chrono::steady_clock::now();
+        uint32_t radius = ORT_PLOC_RADIUS;
+        if(const char *e = getenv("ORT_PLOC_RADIUS")) radius = (uint32_t)atoi(e);
+        if(radius < 1u) radius = 1u;
+        build::DeviceBuildResult built; memset(&built, 0, sizeof(built));
+        bool ok = build::build_on_device(flat, in, radius, &built, &err, dr.d_boxes, dr.d_recs, dr.n_rest);
+        cudaFree(dr.d_boxes); cudaFree(dr.d_recs);
+        if(!ok) return fail(ORT_ERR_CUDA, err);
+        flat.wide_depth = std::max(in.sphere_depth, built.depth);
+        if(flat.wide_depth + 2 > ORT_STACK_SIZE)
+        {
+            cudaFree(built.d_nodes); cudaFree(built.d_prims); cudaFree(built.d_rank_to_prim);
+            return fail(ORT_ERR_LIMIT, "wide BVH deeper than the traversal stack");
+        }
+        flat.info.bvh_node_count = built.node_count;
+        flat.info.bvh_node_bytes = (uint32_t)sizeof(WideNode);
+        bs.build_s = (float)seconds_since(t0);
+        bs.device_build_ms = built.build_ms;
+        bs.ploc_iterations = built.ploc_iterations;
+        bs.wide_depth = flat.wide_depth;
+        return make_scene_handle(flat, built, true, bs, device, scene_out);
+    }
     std::vector<HostPrim> prims;
     rc = collect_records_from_lists(world, lists, &prims, &flat, &err);
     if(rc != ORT_OK) return fail(rc, err);

@@ -650,25 +650,6 @@ inline f3 centre_of_cylinder(const OrtCylinder &c)
     return box_centre(gmin(base - e, other - e), gmax(base + e, other + e));
 }
 
-// the ten octant digits of a shape centre, first level in the top 3 bits of 30
-// (get_bvh_octree_node_child_info, ray.cpp:1476-1522: bit0 = +x, bit1 = +y, bit2 = +z; the child's
-// centre is the parent's -+ half of the parent's half dimension, in float)
-inline uint32_t octant_path(f3 c, f3 node_center, f3 node_half)
-{
-    uint32_t code = 0;
-    for(int level = 0; level < 10; ++level)
-    {
-        f3 h = 0.5f * node_half;
-        uint32_t idx = 0;
-        if(c.x >= node_center.x) { idx |= 1u; node_center.x += h.x; } else node_center.x -= h.x;
-        if(c.y >= node_center.y) { idx |= 2u; node_center.y += h.y; } else node_center.y -= h.y;
-        if(c.z >= node_center.z) { idx |= 4u; node_center.z += h.z; } else node_center.z -= h.z;
-        node_half = h;
-        code = (code << 3) | idx;
-    }
-    return code;
-}
-
 // stable LSD radix sort of (key, payload) pairs on the low `bits` bits of the key
 void radix_sort_pairs(std::vector<uint64_t> &key, std::vector<uint32_t> &val, int bits)
 {
@@ -686,14 +667,6 @@ void radix_sort_pairs(std::vector<uint64_t> &key, std::vector<uint32_t> &val, in
         }
         key.swap(k2); val.swap(v2);
     }
-}
-
-inline int common_levels(uint32_t a, uint32_t b)      // leading 3-bit digits two 30-bit paths share
-{
-    uint32_t x = a ^ b;
-    if(x == 0) return 10;
-    int top = 31 - __builtin_clz(x);                   // highest differing bit, 0..29
-    return (29 - top) / 3;
 }
 
 } // namespace
@@ -737,16 +710,16 @@ int collect_records_from_lists(const OrtWorld *world, const OrtShapeLists *L,
                     {
                         f3 a = v3(mesh.vertices[mesh.indices[3 * k]]), b = v3(mesh.vertices[mesh.indices[3 * k + 1]]), c = v3(mesh.vertices[mesh.indices[3 * k + 2]]);
                         uint64_t i = mesh_first[m] + k;
-                        key[i] = octant_path(box_centre(gmin(gmin(a, b), c), gmax(gmax(a, b), c)), root_center, root_half);
+                        key[i] = build::octant_path(build::triangle_centre(a, b, c), root_center, root_half);
                     }
                 }
             });
         for(auto &th : pool) th.join();
     }
-    for(uint32_t i = 0; i < L->cylinder_count; ++i) key[first_cyl + i] = octant_path(centre_of_cylinder(L->cylinders[i]), root_center, root_half);
-    for(uint32_t i = 0; i < L->box_count; ++i) key[first_box + i] = octant_path(box_centre(v3(L->boxes[i].min), v3(L->boxes[i].max)), root_center, root_half);
-    for(uint32_t i = 0; i < L->sphere_count; ++i) key[first_sph + i] = octant_path(v3(L->spheres[i].center), root_center, root_half);
-    if(L->csg) key[first_csg] = octant_path(box_centre(v3(L->csg->aabb_min), v3(L->csg->aabb_max)), root_center, root_half);
+    for(uint32_t i = 0; i < L->cylinder_count; ++i) key[first_cyl + i] = build::octant_path(centre_of_cylinder(L->cylinders[i]), root_center, root_half);
+    for(uint32_t i = 0; i < L->box_count; ++i) key[first_box + i] = build::octant_path(box_centre(v3(L->boxes[i].min), v3(L->boxes[i].max)), root_center, root_half);
+    for(uint32_t i = 0; i < L->sphere_count; ++i) key[first_sph + i] = build::octant_path(v3(L->spheres[i].center), root_center, root_half);
+    if(L->csg) key[first_csg] = build::octant_path(box_centre(v3(L->csg->aabb_min), v3(L->csg->aabb_max)), root_center, root_half);
     for(uint64_t i = 0; i < n; ++i) who[i] = (uint32_t)i;
 
     // 2. the node of a record is the shortest prefix of its path no other record shares (capped at 10)
@@ -758,8 +731,8 @@ int collect_records_from_lists(const OrtWorld *world, const OrtShapeLists *L,
     for(uint64_t p = 0; p < n; ++p)
     {
         int shared = 0;
-        if(p > 0) shared = std::max(shared, common_levels((uint32_t)sorted_key[p], (uint32_t)sorted_key[p - 1]));
-        if(p + 1 < n) shared = std::max(shared, common_levels((uint32_t)sorted_key[p], (uint32_t)sorted_key[p + 1]));
+        if(p > 0) shared = std::max(shared, build::common_levels((uint32_t)sorted_key[p], (uint32_t)sorted_key[p - 1]));
+        if(p + 1 < n) shared = std::max(shared, build::common_levels((uint32_t)sorted_key[p], (uint32_t)sorted_key[p + 1]));
         int d = n == 1 ? 0 : std::min(shared + 1, 10);
         depth[sorted_who[p]] = (uint8_t)d;
         if((uint32_t)d > max_depth) max_depth = (uint32_t)d;
@@ -844,11 +817,12 @@ int collect_records_from_lists(const OrtWorld *world, const OrtShapeLists *L,
 // pads the primitive boxes (see bvh.h: conservative culling) and separates the spheres, which get
 // a tree of their own, from the rest
 static int pad_and_split(std::vector<HostPrim> &prims, const BuildOptions &opt,
-                         std::vector<HostPrim> *spheres, std::vector<HostPrim> *shapes, std::vector<HostPrim> *tris, std::string *err)
+                         std::vector<HostPrim> *spheres, std::vector<HostPrim> *shapes, std::vector<HostPrim> *tris, std::string *err,
+                         double scene_abs_given = -1.0)
 {
     if(opt.max_leaf < 1 || opt.max_leaf > 3) { *err = "max_leaf must be 1..3"; return ORT_ERR_ARG; }
-    double scene_abs = 0.0;
-    for(size_t i = 0; i < prims.size(); ++i)
+    double scene_abs = scene_abs_given >= 0.0 ? scene_abs_given : 0.0;
+    for(size_t i = 0; scene_abs_given < 0.0 && i < prims.size(); ++i)
         for(int k = 0; k < 3; ++k)
         {
             scene_abs = std::max(scene_abs, fabs((double)prims[i].lo[k]));
@@ -872,13 +846,7 @@ static int pad_and_split(std::vector<HostPrim> &prims, const BuildOptions &opt,
                 p.lo[k] = (float)(c - rr); p.hi[k] = (float)(c + rr);
             }
         }
-        double dx = (double)p.hi[0] - p.lo[0], dy = (double)p.hi[1] - p.lo[1], dz = (double)p.hi[2] - p.lo[2];
-        double pad = opt.pad_rel * sqrt(dx * dx + dy * dy + dz * dz) + opt.pad_scene * scene_abs;
-        for(int k = 0; k < 3; ++k)
-        {
-            p.lo[k] = nextafterf((float)((double)p.lo[k] - pad), -INFINITY);
-            p.hi[k] = nextafterf((float)((double)p.hi[k] + pad), INFINITY);
-        }
+        build::pad_box(p.lo, p.hi, (double)opt.pad_rel, (double)opt.pad_scene * scene_abs);
         if(p.kind == PRIM_SPHERE) spheres->push_back(p);
         else if(p.kind == PRIM_TRIANGLE || opt.merge_shapes) tris->push_back(p);
         else shapes->push_back(p);
@@ -937,6 +905,59 @@ int build_wide_bvh(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatSc
     rc = emit_tree(tris, opt, out, &d2, err);
     if(rc != ORT_OK) return rc;
     return finish_flat_scene(out, std::max(d0, std::max(d1, d2)), err);
+}
+
+// ---- pieces reused by the CUDA execution for the analytic shapes ------------------------------------------
+int fill_world_tables_public(const OrtWorld *world, FlatScene *out, std::string *err) { return fill_world_tables(world, out, err); }
+int pad_and_split_public(std::vector<HostPrim> &prims, const BuildOptions &opt, double scene_abs,
+                         std::vector<HostPrim> *spheres, std::vector<HostPrim> *shapes, std::vector<HostPrim> *tris, std::string *err)
+{
+    return pad_and_split(prims, opt, spheres, shapes, tris, err, scene_abs);
+}
+int emit_tree_public(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, uint32_t *depth_out, std::string *err)
+{
+    return emit_tree(prims, opt, out, depth_out, err);
+}
+PrimRec make_record_public(const HostPrim &hp, FlatScene *out) { return make_record(hp, out); }
+
+// cylinders, boxes, spheres of the lists as records (rank = index among these, to be replaced), and the
+// octant paths of all analytic records, the CSG's last
+int collect_analytic(const OrtWorld *world, const OrtShapeLists *L, f3 root_center, f3 root_half,
+                     std::vector<HostPrim> *analytic, uint32_t *keys, std::string *err)
+{
+    analytic->clear();
+    uint32_t k = 0;
+    for(uint32_t i = 0; i < L->cylinder_count; ++i, ++k)
+    {
+        const OrtCylinder &s = L->cylinders[i];
+        HostPrim p; memset(&p, 0, sizeof(p));
+        p.kind = PRIM_CYLINDER; p.a = v3(s.base); p.b = v3(s.axis); p.radius = s.r; p.mat = s.mat_index; p.rank = k;
+        keys[k] = build::octant_path(centre_of_cylinder(s), root_center, root_half);
+        analytic->push_back(p);
+    }
+    for(uint32_t i = 0; i < L->box_count; ++i, ++k)
+    {
+        const OrtAAB &s = L->boxes[i];
+        HostPrim p; memset(&p, 0, sizeof(p));
+        p.kind = PRIM_AAB; p.a = v3(s.min); p.b = v3(s.max); p.mat = s.mat_index; p.rank = k;
+        keys[k] = build::octant_path(box_centre(v3(s.min), v3(s.max)), root_center, root_half);
+        analytic->push_back(p);
+    }
+    for(uint32_t i = 0; i < L->sphere_count; ++i, ++k)
+    {
+        const OrtSphere &s = L->spheres[i];
+        HostPrim p; memset(&p, 0, sizeof(p));
+        p.kind = PRIM_SPHERE; p.a = v3(s.center); p.radius = s.r; p.mat = s.mat_index; p.rank = k;
+        keys[k] = build::octant_path(v3(s.center), root_center, root_half);
+        analytic->push_back(p);
+    }
+    if(L->csg) keys[k++] = build::octant_path(box_centre(v3(L->csg->aabb_min), v3(L->csg->aabb_max)), root_center, root_half);
+    for(size_t i = 0; i < analytic->size(); ++i)
+    {
+        if((*analytic)[i].mat >= world->mat_count) { *err = "record with material index out of range"; return ORT_ERR_ARG; }
+        prim_bounds((*analytic)[i]);
+    }
+    return ORT_OK;
 }
 
 // ---- the data-parallel builder (bvh_build.h) ---------------------------------------------------------

@@ -86,6 +86,14 @@ struct ParallelBuildInput
 int prepare_parallel_build(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, ParallelBuildInput *in, std::string *err);
 int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOptions &opt, uint32_t radius, FlatScene *out, std::string *err);
 #define ORT_PLOC_RADIUS 16u
+// pieces of the host path the device execution (bvh_build.cuh) reuses for the few analytic shapes
+int collect_analytic(const OrtWorld *world, const OrtShapeLists *lists, f3 root_center, f3 root_half,
+                     std::vector<HostPrim> *analytic, uint32_t *keys, std::string *err);
+int fill_world_tables_public(const OrtWorld *world, FlatScene *out, std::string *err);
+int pad_and_split_public(std::vector<HostPrim> &prims, const BuildOptions &opt, double scene_abs,
+                         std::vector<HostPrim> *spheres, std::vector<HostPrim> *shapes, std::vector<HostPrim> *tris, std::string *err);
+int emit_tree_public(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, uint32_t *depth_out, std::string *err);
+PrimRec make_record_public(const HostPrim &hp, FlatScene *out);
 
 inline int flatten_scene(const OrtWorld *world, const OrtBVHOctreeNode *root, const BuildOptions &opt,
                          FlatScene *out, std::string *err)

@@ -87,8 +87,18 @@ def test_scene_from_shape_lists_on_the_device(ort, testscene_host, tmp_path):
     hs2 = ort.HostScene.load(os.path.join(ol.DATA_DIR, "testscene.scn"), ol.DATA_DIR, hs.width, hs.height, octree=False)
     b = ort.Scene.from_lists(hs2.world, hs2.lists(), 0, build_on_device=True)
     ia, ib = a.info(), b.info()
-    for k in ("triangle_count", "record_count", "octree_node_count", "octree_max_depth", "root_min", "root_max"):
+    for k in ("triangle_count", "sphere_count", "box_count", "cylinder_count", "csg_count", "record_count",
+              "octree_node_count", "octree_max_depth", "material_count", "light_count", "root_min", "root_max"):
         assert ia[k] == ib[k], k
+    # every record carries the rank the octree would have given it: same records in rank order
+    _, pa = a.download()
+    _, pb = b.download()
+    pa = pa[np.argsort(pa[:, 3])]; pb = pb[np.argsort(pb[:, 3])]
+    # (a cylinder's aux index, bits 8.. of the kind word, depends on the order of emission)
+    pa[:, 11] &= 0xFF; pb[:, 11] &= 0xFF
+    assert np.array_equal(pa, pb)
+    st = b.build_stats()
+    assert st["on_device"] == 1 and st["ploc_iterations"] > 5
     o, d = ol.make_incoherent_rays(300000, [-2.9, -2.9, 0.0], [14.9, 14.9, 8.8])
     ra, rb = a.raycast_batch(o, d), b.raycast_batch(o, d)
     assert np.array_equal(ra["rank"], rb["rank"]) and np.array_equal(bits(ra["t"]), bits(rb["t"]))
