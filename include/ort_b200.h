@@ -227,8 +227,11 @@ int ort_render(OrtScene *scene, const OrtCamera *camera, const OrtRenderParams *
 /* Device-resident form for the multi-GPU path: adds the chunk sums of
  * [chunk_begin, chunk_end) into `accum_device`, an int64[height*width*4]
  * fixed-point buffer on the scene's device (zero it first with
- * ort_accum_zero_device), on CUDA stream `stream` (a cudaStream_t passed as
- * void*, NULL = default stream).  After the sum over ranks (ncclSum on int64 is
+ * ort_accum_zero_device).  The work is ordered after whatever the caller queued on
+ * CUDA stream `stream` (a cudaStream_t passed as void*, NULL = default stream); the
+ * call returns when the chunk range is done (the wavefront loop reads its "paths
+ * still alive" counter on the host), so the caller's next launch on any stream
+ * sees the sums.  After the sum over ranks (ncclSum on int64 is
  * exact), ort_accum_resolve_device writes float3 pixels = sum / spp. */
 int ort_render_accumulate_device(OrtScene *scene, const OrtCamera *camera,
                                  const OrtRenderParams *params, void *accum_device,

@@ -656,18 +656,6 @@ k_wf_extend_q(SceneView scene, WfBuffers wf, const uint32_t *__restrict__ rank_t
 
 // ---- counting sort of the slots by shading key -------------------------------------------
 // hist[k] = number of slots with key k; offsets = exclusive scan; perm = slots grouped by key.
-__global__ void __launch_bounds__(256)
-k_wf_hist(WfBuffers wf, uint32_t *hist)
-{
-    __shared__ uint32_t sh[WF_KEY_BINS];
-    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh[k] = 0u;
-    __syncthreads();
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.capacity; i += stride) atomicAdd(&sh[wf.key[i]], 1u);
-    __syncthreads();
-    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) if(sh[k]) atomicAdd(&hist[k], sh[k]);
-}
-
 // one block: exclusive scan of the 512 bins into cursor[], and live = slots that are not dead
 __global__ void __launch_bounds__(512)
 k_wf_scan(const uint32_t *hist, uint32_t *cursor, uint32_t *live)
