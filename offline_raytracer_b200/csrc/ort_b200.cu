@@ -36,7 +36,7 @@ int fail(int code, const std::string &msg)
 } // namespace
 
 #define WF_BATCH 8
-#define WF_MAX_POOLS 2
+#define WF_MAX_POOLS 4
 
 // A pool = a contiguous share of the slots with its own stream, sort scratch and counters.  Two
 // pools run the same loop half a period apart, so that one pool's SHADE (latency-bound) overlaps the
@@ -217,7 +217,9 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
 // iterations, one batch behind the enqueue, so the device never drains while the host decides.
 int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint32_t *launches)
 {
-    uint32_t capacity = 1u << 22;      // 4 Mi slots x 104 B = 416 MB (measured: 1 Mi 636, 2 Mi 707, 4 Mi 720 Msamples/s at 1080p)
+    // 6 Mi slots x 104 B = 650 MB in two pools (measured at 1080p x 256 spp, final kernels, two pools:
+    // 4 Mi 1053, 6 Mi 1066, 8 Mi 1062 Msamples/s; three pools of 2 Mi 1039, four of 2 Mi 1026)
+    uint32_t capacity = 6u << 20;
     if(const char *e = getenv("ORT_WF_SLOTS")) { long v = atol(e); if(v >= 1024 && v <= (1l << 26)) capacity = (uint32_t)v; }
     unsigned long long items128 = (a.total_items + 127ull) & ~127ull;
     if(items128 < capacity) capacity = (uint32_t)items128;
