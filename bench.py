@@ -324,7 +324,10 @@ def main_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic_latest.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                # ncu measured DRAM bytes of ONE launch over `slots_per_launch` rays (profiles/README.md);
+                # per launch here = that per-ray figure x the rays an average launch of this run extends
+                tj = json.load(open(tpath))
+                traffic = tj["dram_bytes_per_launch"] / tj["slots_per_launch"] * (rays / n_extend)
             except Exception:
                 traffic = None
         a = bytes_per_ray * extend_rays_per_s / 1e9
