@@ -363,7 +363,7 @@ def main_gpu(args):
                      "triangles": info["triangle_count"], "records": info["record_count"],
                      "bvh_nodes": info["bvh_node_count"], "scene_device_bytes": info["device_bytes"],
                      "parallelism": "sample-chunk split x%d, ncclReduce(int64 sum)" % world if world > 1 else "1 GPU",
-                     "cache": "L2 flushed between steps (256 MiB memset); the 10 MB scene is re-fetched from HBM each step"},
+                     "cache": "L2 flushed between steps (256 MiB memset); the 5 MB scene is re-fetched from HBM each step"},
           "mrays_per_s": rays_per_s * world / 1e6, "rays_per_sample": rays / max(1, samples),
           "kernel_ms_per_step": kernel_ms, "stage_ms_per_step": {"extend": st["extend_ms"], "sort": st["sort_ms"], "shade": st["shade_ms"]},
           "per_ray_work": per_ray,

@@ -72,7 +72,7 @@ struct OrtScene
     cudaEvent_t ev0, ev1;
     int sm_count;
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
-    int wf_extend_blocks, wf_extend_q_blocks;
+    int wf_extend_blocks;
     uint32_t stack_rows;                // wide-tree depth + 1: rows of the shared-memory traversal stack
     float extend_ms, shade_ms, sort_ms; // summed stage times of the last wavefront render
     // wavefront path pool(s)
@@ -236,12 +236,7 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend<false>, 128, stack_bytes));
         s->wf_extend_blocks = (nb > 0 ? nb : 1) * s->sm_count;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend_q<false>, 128, stack_bytes));
-        s->wf_extend_q_blocks = (nb > 0 ? nb : 1) * s->sm_count;
     }
-    // 0 = k_wf_extend (default); 1 = k_wf_extend_q, the test-redistributing variant -- measured
-    // slower on B200 (238 vs 202 ms of EXTEND per 1080p x 128 spp): rays wait for their queued tests
-    const int extend_q = getenv("ORT_WF_EXTEND") ? atoi(getenv("ORT_WF_EXTEND")) : 0;
     const int extend_blocks_per_sm = getenv("ORT_WF_EXTEND_BPSM") ? atoi(getenv("ORT_WF_EXTEND_BPSM")) : 0;
     s->extend_ms = s->shade_ms = s->sort_ms = 0.f;
     const bool pipelined = a.total_items > 4ull * capacity;
@@ -267,7 +262,7 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     {
         const uint32_t cap = pl.wf.capacity;
         const unsigned grid = (cap + 127u) / 128u;
-        unsigned egrid = (unsigned)(extend_q == 1 ? s->wf_extend_q_blocks : s->wf_extend_blocks);
+        unsigned egrid = (unsigned)s->wf_extend_blocks;
         if(extend_blocks_per_sm > 0 && (unsigned)(extend_blocks_per_sm * s->sm_count) < egrid) egrid = (unsigned)(extend_blocks_per_sm * s->sm_count);
         if(egrid > grid) egrid = grid;
         uint32_t *hist = pl.d_sort, *cursor = pl.d_sort + WF_KEY_BINS, *live = pl.d_sort + 2 * WF_KEY_BINS;
@@ -280,30 +275,11 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
             CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), st));
             CUDA_TRY(cudaMemsetAsync(chunk_counter, 0, sizeof(uint32_t), st));
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][0], st));
-            if(extend_q == 2)
-            {
 #ifdef ORT_COUNTERS
-                k_wf_extend_v<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
+            k_wf_extend<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
 #else
-                k_wf_extend_v<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
+            k_wf_extend<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
 #endif
-            }
-            else if(extend_q)
-            {
-#ifdef ORT_COUNTERS
-                k_wf_extend_q<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
-#else
-                k_wf_extend_q<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, s->d_rank_to_prim, chunk_counter, a.stats, hist);
-#endif
-            }
-            else
-            {
-#ifdef ORT_COUNTERS
-                k_wf_extend<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
-#else
-                k_wf_extend<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
-#endif
-            }
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][1], st));
             if(sorted)
             {

@@ -259,400 +259,12 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
     }
 }
 
-// EXTEND with a warp-wide vote on what to do next.
-//
-// ncu (source page of k_wf_extend, C3 scene): the wide-node visit runs with 27.5 of 32 lanes, but in
-// the primitive loop that follows it the triangle test runs with 1.8 lanes and the box/cylinder test
-// with 9 -- in any one trip only a few rays reach a leaf, and lanes with different kinds of record
-// serialise -- and together they take a third of all issue slots.  Here every trip of the warp does
-// ONE thing: a node visit, one triangle test, or one test of a record of any kind (nodes with a
-// non-triangle record are flagged by the flattener, ORT_NODE_MIXED_KINDS).  A lane that has reached
-// a leaf holds its pending records and takes no further node visit (so its hit bound is as fresh as
-// in k_wf_extend and it visits exactly the same nodes) until the warp votes for its kind of test:
-// when enough lanes wait for it, when it has waited ORT_VOTE_AGE trips, or when no lane has a node
-// to visit.  Results are bit-identical to k_wf_extend.
-#ifndef ORT_VOTE_TRI
-#define ORT_VOTE_TRI 6u
-#endif
-#ifndef ORT_VOTE_MIXED
-#define ORT_VOTE_MIXED 12u
-#endif
-#ifndef ORT_VOTE_AGE
-#define ORT_VOTE_AGE 4u
-#endif
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
-k_wf_extend_v(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned long long *stats, uint32_t *hist)
-{
-    extern __shared__ uint2 smem_stack[];
-    __shared__ uint32_t sh_hist[WF_KEY_BINS];
-    __shared__ uint32_t sh_done;
-    if(threadIdx.x == 0) sh_done = 0u;
-    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh_hist[k] = 0u;
-    __syncthreads();
-    SharedStack st; st.col = smem_stack + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t next = 0u, end = 0u;
-    bool exhausted = false;
-
-    Trav t;
-    t.ng_x = t.ng_y = 0u; t.sp = 0;
-    bool has_ray = false;
-    uint32_t slot = 0u, is_primary = 0u;
-    uint32_t pg_x = 0u, pg_y = 0u, pg_mixed = 0u;          // pending records of the leaf children just reached
-    uint32_t tri_wait = 0u, mixed_wait = 0u;               // warp-uniform: trips the waiting lanes have been held
-    unsigned long long nodes = 0, boxes = 0, shapes = 0, rays = 0;
-
-    for(;;)
-    {
-        uint32_t idle_mask = __ballot_sync(0xFFFFFFFFu, !has_ray);
-        if(!exhausted && (__popc(idle_mask) >= ORT_FETCH_MIN || idle_mask == 0xFFFFFFFFu))
-        {
-            if(next >= end)
-            {
-                uint32_t base = 0u;
-                if(lane == 0) base = atomicAdd(chunk_counter, WF_CHUNK);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                next = base; end = base + WF_CHUNK;
-                if(end > wf.capacity) end = wf.capacity;
-                if(base >= wf.capacity) { exhausted = true; next = end = 0u; }
-            }
-            uint32_t my = next + __popc(idle_mask & ((1u << lane) - 1u));
-            if(!has_ray && my < end)
-            {
-                float4 ro = wf.rec[WF_REC_QUADS * my], rd = wf.rec[WF_REC_QUADS * my + 1u];      // one sector, one round trip
-                if(wf_state_of(__float_as_uint(rd.w)) == WF_ACTIVE)
-                {
-                    trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
-                    is_primary = __float_as_uint(rd.w) >> 31;
-                    slot = my;
-                    has_ray = true;
-                    pg_y = 0u;
-                    ++rays;
-                }
-                else { wf.key[my] = WF_KEY_DEAD; atomicAdd(&sh_hist[WF_KEY_DEAD], 1u); }
-            }
-            next += __popc(idle_mask);
-            if(next > end) next = end;
-        }
-        const bool w_visit = has_ray && pg_y == 0u;
-        const bool w_tri = has_ray && pg_y != 0u && pg_mixed == 0u;
-        const bool w_mixed = has_ray && pg_y != 0u && pg_mixed != 0u;
-        const uint32_t n_visit = __popc(__ballot_sync(0xFFFFFFFFu, w_visit));
-        const uint32_t n_tri = __popc(__ballot_sync(0xFFFFFFFFu, w_tri));
-        const uint32_t n_mixed = __popc(__ballot_sync(0xFFFFFFFFu, w_mixed));
-        if((n_visit | n_tri | n_mixed) == 0u)
-        {
-            if(exhausted) break;
-            continue;
-        }
-        uint32_t action;          // 0 visit, 1 triangle test, 2 test of any kind
-        if(n_tri != 0u && (n_tri >= ORT_VOTE_TRI || tri_wait >= ORT_VOTE_AGE)) action = 1u;
-        else if(n_mixed != 0u && (n_mixed >= ORT_VOTE_MIXED || mixed_wait >= ORT_VOTE_AGE)) action = 2u;
-        else if(n_visit != 0u) action = 0u;
-        else action = n_tri >= n_mixed ? 1u : 2u;
-        tri_wait = (action == 1u || n_tri == 0u) ? 0u : tri_wait + 1u;
-        mixed_wait = (action == 2u || n_mixed == 0u) ? 0u : mixed_wait + 1u;
-
-        if(action == 0u)
-        {
-            if(w_visit)
-            {
-                TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
-                uint32_t node_index;
-                trav_visit<COUNT>(scene, t, st, t.best_t, &cnt, &pg_x, &pg_y, &node_index, &pg_mixed);
-                if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; }
-            }
-        }
-        else if(action == 1u)
-        {
-            if(w_tri)
-            {
-                uint32_t prim = pg_x + lsb32(pg_y);
-                pg_y &= pg_y - 1u;
-                const q4 *p = scene.prims + 3u * prim;
-                q4 A = ldq(p), B = ldq(p + 1), C = ldq(p + 2);
-                exact::Hit h = exact::triangle(q3(A), q3(B), q3(C), t.o, t.d);
-                uint32_t rank = f2u(A.w);
-                if(COUNT) ++shapes;
-                if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < t.best_t || (h.t == t.best_t && rank < t.best_rank)))
-                {
-                    t.best_t = h.t; t.best_prim = prim; t.best_rank = rank;
-                }
-            }
-        }
-        else
-        {
-            if(w_mixed)
-            {
-                uint32_t prim = pg_x + lsb32(pg_y), rank, mat;
-                pg_y &= pg_y - 1u;
-                exact::Hit h = intersect_prim(scene, prim, t.o, t.d, t.inv, &rank, &mat);
-                (void)mat;
-                if(COUNT) ++shapes;
-                if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < t.best_t || (h.t == t.best_t && rank < t.best_rank)))
-                {
-                    t.best_t = h.t; t.best_prim = prim; t.best_rank = rank;
-                }
-            }
-        }
-        // a ray with no pending record and no node left in its group pops the stack, or is done
-        if(has_ray && pg_y == 0u && !trav_next(t, st))
-        {
-            uint32_t mat = 0u;
-            if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
-            wf_store_hit(wf, slot, t.best_t, t.best_prim, mat);
-            uint32_t key = (is_primary ? 256u : 0u) | (mat < 254u ? mat : 254u);
-            wf.key[slot] = key;
-            atomicAdd(&sh_hist[key], 1u);
-            has_ray = false;
-        }
-    }
-    rays = warp_sum(rays);
-    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); shapes = warp_sum(shapes); }
-    if(lane == 0 && rays)
-    {
-        atomicAdd(&stats[STAT_RAYS], rays);
-        if(COUNT)
-        {
-            atomicAdd(&stats[STAT_NODE_VISITS], nodes);
-            atomicAdd(&stats[STAT_BOX_TESTS], boxes);
-            atomicAdd(&stats[STAT_SHAPE_TESTS], shapes);
-        }
-    }
-    __syncwarp();
-    uint32_t finished = 0u;
-    if(lane == 0) { __threadfence_block(); finished = atomicAdd(&sh_done, 1u); }
-    finished = __shfl_sync(0xFFFFFFFFu, finished, 0);
-    if(finished == 3u)
-    {
-        __threadfence_block();
-        for(uint32_t k = lane; k < WF_KEY_BINS; k += 32u)
-        {
-            uint32_t v = ((volatile uint32_t *)sh_hist)[k];
-            if(v) atomicAdd(&hist[k], v);
-        }
-    }
-}
-
-// EXTEND with primitive-test redistribution.
-//
-// ncu (source page of the kernel above, C3 scene): the wide-node visit runs with 28.8 of 32 lanes,
-// but the primitive tests that follow it run with 1.4-8 lanes -- in any one trip only a few rays
-// of a warp reach a leaf -- and take a third of all issue slots.  Here a lane does not test the
-// primitives its ray reaches; it appends (owner lane, primitive) to a per-warp queue in shared
-// memory, one queue per primitive kind (triangles / analytic shapes: the node's tree tells).  When
-// a queue holds 32 entries -- or the warp is running out of node work -- lane L tests entry L,
-// fetching the owner's ray with shuffles, and folds the result into the owner's best hit with a
-// 64-bit shared-memory atomicMin on (t bits << 32 | rank): t > 0, so the float bits order like
-// the floats, and the low word breaks exact-t ties by rank -- the reference's "first tested
-// wins".  Culling reads the same word, so it only ever uses a bound that is already proven.
-// Slot ranges are handed out in chunks from a global counter, so warps finish together.
-#define WF_QCAP 128u
-#ifndef ORT_Q_BUSY
-#define ORT_Q_BUSY 16u       // partial batches wait while at least this many lanes still have node work (33 = never wait)
-#endif
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
-k_wf_extend_q(SceneView scene, WfBuffers wf, const uint32_t *__restrict__ rank_to_prim, uint32_t *chunk_counter,
-              unsigned long long *stats, uint32_t *hist)
-{
-    extern __shared__ uint2 smem_stack[];
-    __shared__ uint32_t sh_hist[WF_KEY_BINS];
-    __shared__ unsigned long long sh_best[128];
-    __shared__ uint32_t sh_queue[4][2][WF_QCAP];
-    __shared__ uint32_t sh_done;
-    if(threadIdx.x == 0) sh_done = 0u;
-    for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) sh_hist[k] = 0u;
-    __syncthreads();
-    SharedStack st; st.col = smem_stack + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    unsigned long long *my_best = sh_best + threadIdx.x;
-    unsigned long long *warp_best = sh_best + (wib << 5);
-    uint32_t (*queue)[WF_QCAP] = sh_queue[wib];
-
-    Trav t;
-    t.ng_x = t.ng_y = 0u; t.sp = 0;
-    t.o = t.d = t.inv = mk3(0.f, 0.f, 0.f);
-    bool has_ray = false, node_active = false;
-    uint32_t slot = 0u, is_primary = 0u;
-    uint32_t q_head[2] = { 0u, 0u }, q_tail[2] = { 0u, 0u };      // warp-uniform sequence numbers
-    uint32_t my_last[2] = { 0u, 0u };                             // sequence just past my last entry
-    uint32_t next = 0u, end = 0u;
-    bool exhausted = false;
-    unsigned long long nodes = 0, boxes = 0, shapes = 0, rays = 0;
-
-    for(;;)
-    {
-        // ---- 1. hand new rays to free lanes ----
-        uint32_t free_mask = __ballot_sync(0xFFFFFFFFu, !has_ray);
-        if(free_mask != 0u && !exhausted)
-        {
-            if(next >= end)
-            {
-                uint32_t base = 0u;
-                if(lane == 0) base = atomicAdd(chunk_counter, WF_CHUNK);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                next = base; end = base + WF_CHUNK;
-                if(end > wf.capacity) end = wf.capacity;
-                if(base >= wf.capacity) { exhausted = true; next = end = 0u; }
-            }
-            if(!exhausted)
-            {
-                uint32_t my = next + __popc(free_mask & lt_mask);
-                if(!has_ray && my < end)
-                {
-                    float4 ro = wf.rec[WF_REC_QUADS * my], rd = wf.rec[WF_REC_QUADS * my + 1u];      // one sector, one round trip
-                    if(wf_state_of(__float_as_uint(rd.w)) == WF_ACTIVE)
-                    {
-                        trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
-                        is_primary = __float_as_uint(rd.w) >> 31;
-                        slot = my;
-                        has_ray = true; node_active = true;
-                        *my_best = 0x7F7FFFFFFFFFFFFFull;          // (FLT_MAX, MISS)
-                        my_last[0] = q_head[0]; my_last[1] = q_head[1];
-                        ++rays;
-                    }
-                    else { wf.key[my] = WF_KEY_DEAD; atomicAdd(&sh_hist[WF_KEY_DEAD], 1u); }
-                }
-                next += __popc(free_mask);
-                if(next > end) next = end;
-            }
-        }
-        uint32_t ray_mask = __ballot_sync(0xFFFFFFFFu, has_ray);
-        if(ray_mask == 0u)
-        {
-            if(exhausted) break;
-            continue;
-        }
-
-        // ---- 2. one wide-node visit per lane; the leaves it reaches go to the queues ----
-        uint32_t tg_x = 0u, tg_y = 0u, kind = 0u;
-        if(node_active)
-        {
-            TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
-            uint32_t node_index;
-            float clip = __uint_as_float((uint32_t)(*my_best >> 32));
-            trav_visit<COUNT>(scene, t, st, clip, &cnt, &tg_x, &tg_y, &node_index);
-            kind = node_index < scene.tri_root ? 1u : 0u;
-            node_active = trav_next(t, st);
-            if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; shapes += popc32(tg_y); }
-        }
-        for(;;)
-        {
-            uint32_t m0 = __ballot_sync(0xFFFFFFFFu, tg_y != 0u && kind == 0u);
-            uint32_t m1 = __ballot_sync(0xFFFFFFFFu, tg_y != 0u && kind == 1u);
-            if((m0 | m1) == 0u) break;
-            // keep room for 32 appends: drain full batches first
-#pragma unroll
-            for(int q = 0; q < 2; ++q)
-            {
-                uint32_t m = q ? m1 : m0;
-                if(m == 0u) continue;
-                while(q_tail[q] - q_head[q] + 32u > WF_QCAP)
-                {
-                    // (drain: same code as step 3 below, full batch)
-                    uint32_t e = queue[q][(q_head[q] + lane) % WF_QCAP];
-                    uint32_t owner = e >> 27, prim = e & 0x07FFFFFFu;
-                    f3 o = mk3(__shfl_sync(0xFFFFFFFFu, t.o.x, owner), __shfl_sync(0xFFFFFFFFu, t.o.y, owner), __shfl_sync(0xFFFFFFFFu, t.o.z, owner));
-                    f3 d = mk3(__shfl_sync(0xFFFFFFFFu, t.d.x, owner), __shfl_sync(0xFFFFFFFFu, t.d.y, owner), __shfl_sync(0xFFFFFFFFu, t.d.z, owner));
-                    f3 inv = mk3(__shfl_sync(0xFFFFFFFFu, t.inv.x, owner), __shfl_sync(0xFFFFFFFFu, t.inv.y, owner), __shfl_sync(0xFFFFFFFFu, t.inv.z, owner));
-                    uint32_t rank, mat;
-                    exact::Hit h = intersect_prim(scene, prim, o, d, inv, &rank, &mat);
-                    if(h.t >= ORT_HIT_T_THRESHOLD)
-                        atomicMin(warp_best + owner, ((unsigned long long)__float_as_uint(h.t) << 32) | rank);
-                    q_head[q] += 32u;
-                    __syncwarp();
-                }
-                if(tg_y != 0u && kind == (uint32_t)q)
-                {
-                    uint32_t bit = lsb32(tg_y);
-                    tg_y &= tg_y - 1u;
-                    uint32_t pos = q_tail[q] + __popc(m & lt_mask);
-                    queue[q][pos % WF_QCAP] = (lane << 27) | (tg_x + bit);
-                    my_last[q] = pos + 1u;
-                }
-                q_tail[q] += __popc(m);
-            }
-            __syncwarp();
-        }
-
-        // ---- 3. run queued tests: full batches always, partial ones when node work runs low ----
-        uint32_t busy = __popc(__ballot_sync(0xFFFFFFFFu, node_active));
-#pragma unroll
-        for(int q = 0; q < 2; ++q)
-        {
-            for(;;)
-            {
-                uint32_t count = q_tail[q] - q_head[q];
-                if(count == 0u) break;
-                if(count < 32u && busy >= ORT_Q_BUSY) break;
-                uint32_t n = count < 32u ? count : 32u;
-                uint32_t e = queue[q][(q_head[q] + lane) % WF_QCAP];
-                uint32_t owner = (e >> 27), prim = e & 0x07FFFFFFu;
-                if(lane >= n) owner = lane;
-                f3 o = mk3(__shfl_sync(0xFFFFFFFFu, t.o.x, owner), __shfl_sync(0xFFFFFFFFu, t.o.y, owner), __shfl_sync(0xFFFFFFFFu, t.o.z, owner));
-                f3 d = mk3(__shfl_sync(0xFFFFFFFFu, t.d.x, owner), __shfl_sync(0xFFFFFFFFu, t.d.y, owner), __shfl_sync(0xFFFFFFFFu, t.d.z, owner));
-                f3 inv = mk3(__shfl_sync(0xFFFFFFFFu, t.inv.x, owner), __shfl_sync(0xFFFFFFFFu, t.inv.y, owner), __shfl_sync(0xFFFFFFFFu, t.inv.z, owner));
-                if(lane < n)
-                {
-                    uint32_t rank, mat;
-                    exact::Hit h = intersect_prim(scene, prim, o, d, inv, &rank, &mat);
-                    if(h.t >= ORT_HIT_T_THRESHOLD)
-                        atomicMin(warp_best + owner, ((unsigned long long)__float_as_uint(h.t) << 32) | rank);
-                }
-                q_head[q] += n;
-                __syncwarp();
-            }
-        }
-
-        // ---- 4. rays with no node work left and all their tests done are finished ----
-        if(has_ray && !node_active && (int)(q_head[0] - my_last[0]) >= 0 && (int)(q_head[1] - my_last[1]) >= 0)
-        {
-            unsigned long long best = *my_best;
-            uint32_t rank = (uint32_t)best, prim = 0xFFFFFFFFu, mat = 0u;
-            if(rank != 0xFFFFFFFFu)
-            {
-                prim = rank_to_prim[rank];
-                mat = f2u(ldq(scene.prims + 3u * prim + 1u).w);
-            }
-            wf_store_hit(wf, slot, __uint_as_float((uint32_t)(best >> 32)), prim, mat);
-            uint32_t key = (is_primary ? 256u : 0u) | (mat < 254u ? mat : 254u);
-            wf.key[slot] = key;
-            atomicAdd(&sh_hist[key], 1u);
-            has_ray = false;
-        }
-    }
-    rays = warp_sum(rays);
-    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); shapes = warp_sum(shapes); }
-    if(lane == 0 && rays)
-    {
-        atomicAdd(&stats[STAT_RAYS], rays);
-        if(COUNT)
-        {
-            atomicAdd(&stats[STAT_NODE_VISITS], nodes);
-            atomicAdd(&stats[STAT_BOX_TESTS], boxes);
-            atomicAdd(&stats[STAT_SHAPE_TESTS], shapes);
-        }
-    }
-    // the block's share of the key histogram, flushed by whichever warp finishes last (no barrier)
-    __syncwarp();
-    uint32_t finished = 0u;
-    if(lane == 0) { __threadfence_block(); finished = atomicAdd(&sh_done, 1u); }
-    finished = __shfl_sync(0xFFFFFFFFu, finished, 0);
-    if(finished == 3u)
-    {
-        __threadfence_block();
-        for(uint32_t k = lane; k < WF_KEY_BINS; k += 32u)
-        {
-            uint32_t v = ((volatile uint32_t *)sh_hist)[k];
-            if(v) atomicAdd(&hist[k], v);
-        }
-    }
-}
+// Two other schedulings of this kernel were built, measured on B200 and removed (profiles/README.md,
+// "tried and rejected"; the code is in the history: commits a82c651 and 1bcd9df): primitive tests
+// redistributed over the lanes of a warp through shared-memory queues (238 vs 202 ms of EXTEND, 213 when
+// drained at once) and a warp-wide vote on the next action -- node visit, triangle test or any test --
+// with lanes holding their pending records (212-224 vs 168 ms).  Both were bit-identical to this kernel;
+// in both the extra trips, ballots and shuffles cost more than the fuller primitive tests saved.
 
 // ---- counting sort of the slots by shading key -------------------------------------------
 // hist[k] = number of slots with key k; offsets = exclusive scan; perm = slots grouped by key.

@@ -204,13 +204,9 @@ def test_wavefront_small_pool_and_unsorted_give_the_same_image(ort, testscene_ho
     monkeypatch.setenv("ORT_WF_NOSORT", "1")
     unsorted, _ = sc.render(testscene_host.camera, P)
     assert np.array_equal(bits(base), bits(unsorted))
-    monkeypatch.delenv("ORT_WF_NOSORT"); monkeypatch.setenv("ORT_WF_EXTEND", "1")
-    queued, _ = sc.render(testscene_host.camera, P)
-    assert np.array_equal(bits(base), bits(queued))
-    for variant in ("0", "2"):      # plain per-lane loop / warp-vote scheduling
-        monkeypatch.setenv("ORT_WF_EXTEND", variant)
-        img, _ = sc.render(testscene_host.camera, P)
-        assert np.array_equal(bits(base), bits(img)), variant
+    monkeypatch.delenv("ORT_WF_NOSORT"); monkeypatch.setenv("ORT_WF_POOLS", "1")
+    one_pool, _ = sc.render(testscene_host.camera, P)
+    assert np.array_equal(bits(base), bits(one_pool))
     sc.close()
 
 

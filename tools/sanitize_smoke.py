@@ -24,12 +24,12 @@ g = sc.raycast_batch(np.concatenate([o, o2]), np.concatenate([d, d2]))
 print("raycast ok", int((g["mat"] != 0).sum()))
 for kernel in (ort.ORT_KERNEL_MEGAKERNEL, ort.ORT_KERNEL_WAVEFRONT):
     for chunk in (0, 2):
-        for env in ({}, {"ORT_WF_EXTEND": "1"}):
-            os.environ.pop("ORT_WF_EXTEND", None)
+        for env in ({}, {"ORT_WF_POOLS": "1"}):
+            os.environ.pop("ORT_WF_POOLS", None)
             os.environ.update(env)
             img, st = sc.render(hs.camera, ort.default_params(W, H, 4, chunk_spp=chunk, kernel=kernel))
             print("render ok kernel", kernel, "chunk", chunk, env, "mean", img.mean((0, 1)), "launches", st["kernel_launches"])
-os.environ.pop("ORT_WF_EXTEND", None)
+os.environ.pop("ORT_WF_POOLS", None)
 import torch  # noqa: E402
 n = 2000
 to = torch.from_numpy(o2[:n]).cuda(); td = torch.from_numpy(d2[:n]).cuda()
