@@ -57,6 +57,16 @@ __global__ void k_ploc_apply(uint32_t n, const uint32_t *__restrict__ nn, const 
     if(i < n) ploc_apply(i, nn, cluster, fate[i], pos[i], mid[i], next_node, nodes, sizes, cost, new_cluster, max_leaf, traversal_cost);
 }
 
+// the clusters still alive: their nodes, sizes and costs, packed for the host's top-tree build
+__global__ void k_pack_clusters(uint32_t count, const uint32_t *__restrict__ cluster, const B2 *__restrict__ nodes,
+                                const uint32_t *__restrict__ sizes, const float *__restrict__ cost, B2 *out_nodes, uint32_t *out_sizes, float *out_cost)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= count) return;
+    uint32_t id = cluster[i];
+    out_nodes[i] = nodes[id]; out_sizes[i] = sizes[id]; out_cost[i] = cost[id];
+}
+
 __global__ void k_gather(uint32_t n_items, const Item *__restrict__ items, const B2 *__restrict__ nodes, const uint32_t *__restrict__ sizes,
                          uint32_t max_leaf, Kids *kids, uint32_t *n_inner, uint32_t *n_prims)
 {
@@ -177,7 +187,8 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
         k_init_leaves<<<G(n), T>>>(n, d_order, d_boxes, d_b2, d_sizes, d_cost, d_cluster);
         {
             uint32_t count = n, next_node = n;
-            while(count > 1)
+            const uint32_t top_k = parallel_top_clusters(n);
+            while(count > std::max(1u, top_k))
             {
                 k_ploc_nearest<<<G(count), T>>>(count, d_cluster, d_b2, radius, d_nn);
                 k_ploc_fate<<<G(count), T>>>(count, d_nn, d_fate, d_keep, d_merge);
@@ -197,6 +208,34 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
                 next_node += merged; count = kept;
                 std::swap(d_cluster, d_cluster2);
                 ++iterations;
+            }
+            if(count > 1)
+            {
+                // the top of the tree: binned SAH over the remaining clusters, on the host (scene_flatten.cpp)
+                std::vector<B2> hn(2 * (size_t)count); std::vector<uint32_t> hs(2 * (size_t)count, 0u), hc(count); std::vector<float> hcost(2 * (size_t)count, 0.f);
+                B2 *d_pn = (B2 *)d_kids;                                   // scratch: the collapse has not started yet
+                uint32_t *d_ps = d_keep; float *d_pc = (float *)d_merge;
+                k_pack_clusters<<<G(count), T>>>(count, d_cluster, d_b2, d_sizes, d_cost, d_pn, d_ps, d_pc);
+                BUILD_TRY(cudaMemcpy(hn.data(), d_pn, (size_t)count * sizeof(B2), cudaMemcpyDeviceToHost));
+                BUILD_TRY(cudaMemcpy(hs.data(), d_ps, (size_t)count * 4, cudaMemcpyDeviceToHost));
+                BUILD_TRY(cudaMemcpy(hcost.data(), d_pc, (size_t)count * 4, cudaMemcpyDeviceToHost));
+                BUILD_TRY(cudaMemcpy(hc.data(), d_cluster, (size_t)count * 4, cudaMemcpyDeviceToHost));
+                std::vector<uint32_t> local(count);
+                for(uint32_t c = 0; c < count; ++c) local[c] = c;
+                uint32_t local_next = count, local_root = 0;
+                BuildOptions o; o.traversal_cost = in.traversal_cost; o.max_leaf = in.max_leaf;
+                if(build_top_tree(local, o, in.max_leaf, in.traversal_cost, hn.data(), hs.data(), hcost.data(), &local_next, &local_root, err) != ORT_OK)
+                { ok = false; goto done; }
+                // local ids -> global ids: clusters keep theirs, new nodes follow next_node
+                auto global_id = [&](uint32_t l) { return l < count ? hc[l] : next_node + (l - count); };
+                const uint32_t added = local_next - count;
+                for(uint32_t j = count; j < local_next; ++j) { hn[j].left = global_id(hn[j].left); hn[j].right = global_id(hn[j].right); }
+                BUILD_TRY(cudaMemcpy(d_b2 + next_node, hn.data() + count, (size_t)added * sizeof(B2), cudaMemcpyHostToDevice));
+                BUILD_TRY(cudaMemcpy(d_sizes + next_node, hs.data() + count, (size_t)added * 4, cudaMemcpyHostToDevice));
+                BUILD_TRY(cudaMemcpy(d_cost + next_node, hcost.data() + count, (size_t)added * 4, cudaMemcpyHostToDevice));
+                uint32_t root_global = global_id(local_root);
+                BUILD_TRY(cudaMemcpy(d_cluster, &root_global, 4, cudaMemcpyHostToDevice));
+                next_node += added; count = 1;
             }
         }
         // 3. collapse to 8-wide, level by level

@@ -8,8 +8,11 @@
 //   2. PLOC (parallel locally-ordered clustering, Meister & Bittner 2018): every cluster looks
 //      `radius` entries left and right in the Morton order for the neighbour whose union with it
 //      has the smallest surface area; mutual choices merge into a binary node; a prefix sum
-//      compacts the cluster list; repeat until one cluster is left.  Agglomerative, so the tree
-//      quality is that of a SAH build rather than of a spatial-median LBVH.
+//      compacts the cluster list; repeat until few clusters are left (at most 65536, at most n / 64).
+//      Agglomerative, so the quality of the bottom of the tree is that of a SAH build rather than of
+//      a spatial-median LBVH; its weak spot is the top -- it only ever looks at Morton neighbours --
+//      so the last clusters are joined top-down by the host's binned-SAH builder (a few thousand
+//      boxes, milliseconds): node visits per ray on the 4.4 M-triangle grid 9.76 -> 9.13 (SAH 8.73).
 //   3. Collapse to 8-wide, level by level: each wide node opens its largest inner binary child until
 //      it has 8; binary subtrees of <= max_leaf primitives become leaf children.  Children are
 //      assigned to octant slots, their boxes quantised outward to the node's 8-bit grid
@@ -155,16 +158,9 @@ ORT_HD uint32_t ploc_fate(uint32_t i, const uint32_t *nn)
 #define B2_LEAF_FLAG 0x80000000u
 ORT_HD uint32_t subtree_size(const uint32_t *sizes, uint32_t id) { return sizes[id] & ~B2_LEAF_FLAG; }
 
-// writes the new cluster entry of i (pos = its index in the compacted list, mid = how many merges
-// precede it)
-ORT_HD void ploc_apply(uint32_t i, const uint32_t *nn, const uint32_t *cluster, uint32_t fate, uint32_t pos, uint32_t mid,
-                       uint32_t next_node, B2 *nodes, uint32_t *sizes, float *cost, uint32_t *new_cluster,
-                       uint32_t max_leaf, float traversal_cost)
+// binary node `id` = parent of l and r: box, size, SAH cost and the leaf decision
+ORT_HD void merge_nodes(uint32_t id, uint32_t l, uint32_t r, B2 *nodes, uint32_t *sizes, float *cost, uint32_t max_leaf, float traversal_cost)
 {
-    if(fate == 0u) return;
-    if(fate == 1u) { new_cluster[pos] = cluster[i]; return; }
-    uint32_t l = cluster[i], r = cluster[nn[i]];
-    uint32_t id = next_node + mid;
     B2 a = nodes[l], b = nodes[r], m;
     for(int k = 0; k < 3; ++k)
     {
@@ -179,6 +175,19 @@ ORT_HD void ploc_apply(uint32_t i, const uint32_t *nn, const uint32_t *cluster, 
     bool leaf = count <= max_leaf && as_leaf <= as_inner;
     sizes[id] = count | (leaf ? B2_LEAF_FLAG : 0u);
     cost[id] = (float)(leaf ? as_leaf : as_inner);
+}
+
+// writes the new cluster entry of i (pos = its index in the compacted list, mid = how many merges
+// precede it)
+ORT_HD void ploc_apply(uint32_t i, const uint32_t *nn, const uint32_t *cluster, uint32_t fate, uint32_t pos, uint32_t mid,
+                       uint32_t next_node, B2 *nodes, uint32_t *sizes, float *cost, uint32_t *new_cluster,
+                       uint32_t max_leaf, float traversal_cost)
+{
+    if(fate == 0u) return;
+    if(fate == 1u) { new_cluster[pos] = cluster[i]; return; }
+    uint32_t l = cluster[i], r = cluster[nn[i]];
+    uint32_t id = next_node + mid;
+    merge_nodes(id, l, r, nodes, sizes, cost, max_leaf, traversal_cost);
     new_cluster[pos] = id;
 }
 

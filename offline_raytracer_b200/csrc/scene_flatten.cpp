@@ -1004,6 +1004,50 @@ int prepare_parallel_build(std::vector<HostPrim> &prims, const BuildOptions &opt
     return ORT_OK;
 }
 
+// PLOC's weak spot is the top of the tree (it only ever looks at Morton neighbours); once few clusters
+// are left, the rest is built top-down with the binned-SAH builder over the cluster boxes -- a few
+// thousand items, milliseconds on the host -- and appended to the binary node array.
+uint32_t parallel_top_clusters(uint32_t n)
+{
+    uint32_t k = ORT_PLOC_TOP_CLUSTERS;
+    if(const char *e = getenv("ORT_PLOC_TOP")) k = (uint32_t)atoi(e);
+    return std::min(k, n / 64u);          // clustering does the bulk of the work whatever the scene size
+}
+
+int build_top_tree(const std::vector<uint32_t> &clusters, const BuildOptions &opt, uint32_t max_leaf, float traversal_cost,
+                   build::B2 *nodes, uint32_t *sizes, float *cost, uint32_t *next_node, uint32_t *root_out, std::string *err)
+{
+    std::vector<HostPrim> items(clusters.size());
+    for(size_t c = 0; c < clusters.size(); ++c)
+    {
+        memset(&items[c], 0, sizeof(HostPrim));
+        for(int k = 0; k < 3; ++k) { items[c].lo[k] = nodes[clusters[c]].lo[k]; items[c].hi[k] = nodes[clusters[c]].hi[k]; }
+    }
+    BuildOptions o = opt; o.max_leaf = 1;
+    Builder tb(items, o);
+    tb.build();
+    // children are allocated after their parent: walk the nodes backwards
+    std::vector<uint32_t> id_of(tb.nodes.size(), 0u);
+    for(size_t i = tb.nodes.size(); i-- > 0; )
+    {
+        const B2Node &nd = tb.nodes[i];
+        if(nd.count > 0)
+        {
+            if(nd.count != 1) { *err = "internal: top tree leaf with several clusters"; return ORT_ERR_LIMIT; }
+            id_of[i] = clusters[tb.idx[nd.first]];
+        }
+        else
+        {
+            if(nd.left <= i || nd.right <= i) { *err = "internal: top tree node order"; return ORT_ERR_LIMIT; }
+            uint32_t id = (*next_node)++;
+            build::merge_nodes(id, id_of[nd.left], id_of[nd.right], nodes, sizes, cost, max_leaf, traversal_cost);
+            id_of[i] = id;
+        }
+    }
+    *root_out = id_of[0];
+    return ORT_OK;
+}
+
 // Host execution of bvh_build.h: plain loops over the same per-element functions the CUDA kernels
 // call, in the same order.  Test infrastructure (tests/sim): it pins what the kernels must produce.
 int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOptions &opt, uint32_t radius, FlatScene *out, std::string *err)
@@ -1040,7 +1084,8 @@ int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOption
         nodes[i] = l; sizes[i] = 1u | B2_LEAF_FLAG; cost[i] = (float)half_area(l); cluster[i] = i;
     }
     uint32_t count = n, next_node = n;
-    while(count > 1)
+    const uint32_t top_k = parallel_top_clusters(n);
+    while(count > std::max(1u, top_k))
     {
         for(uint32_t i = 0; i < count; ++i) nn[i] = ploc_nearest(i, count, cluster.data(), nodes.data(), radius);
         for(uint32_t i = 0; i < count; ++i) fate[i] = ploc_fate(i, nn.data());
@@ -1053,6 +1098,14 @@ int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOption
         }
         next_node += mid; count = pos;
         cluster.swap(next_cluster);
+    }
+    if(count > 1)
+    {
+        uint32_t top_root = 0;
+        std::vector<uint32_t> live(cluster.begin(), cluster.begin() + count);
+        rc = build_top_tree(live, opt, in.max_leaf, in.traversal_cost, nodes.data(), sizes.data(), cost.data(), &next_node, &top_root, err);
+        if(rc != ORT_OK) return rc;
+        cluster[0] = top_root;
     }
     const uint32_t root = cluster[0];
     // 3. collapse, level by level
