@@ -91,8 +91,11 @@ int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_nod
  * CUDA kernels (csrc/bvh_build.h/.cuh) instead of the host's binned-SAH builder -- the replacement
  * for the minutes the reference spends in push_shape_inside_node / validate_nodes_and_reallocate_shapes
  * (code/ray.cpp:1799-2045) on large scenes.  Hits are bit-identical either way: the structure only
- * decides which records are tested.  ort_scene_create honours ORT_BVH_BUILD=device in the environment. */
+ * decides which records are tested.  ort_scene_create = ORT_BUILD_AUTO unless the environment says
+ * ORT_BVH_BUILD=host or =device. */
 #define ORT_BUILD_ON_DEVICE 1u
+#define ORT_BUILD_AUTO 2u               /* on the device when the scene has ORT_BUILD_AUTO_RECORDS records or more */
+#define ORT_BUILD_AUTO_RECORDS 1000000u
 int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node,
                         int device, uint32_t flags, OrtScene **scene_out);
 

@@ -96,6 +96,7 @@ class BuildStats(C.Structure):
 
 
 ORT_BUILD_ON_DEVICE = 1
+ORT_BUILD_AUTO = 2
 
 _lib = None
 
@@ -266,13 +267,14 @@ class Scene:
         self.device = device
 
     @classmethod
-    def from_lists(cls, world_ptr, lists, device=0, build_on_device=False, library=None):
-        """ort_scene_create_from_lists: no octree needed; `lists` is a ShapeLists (HostScene.lists())"""
+    def from_lists(cls, world_ptr, lists, device=0, build_on_device=None, library=None):
+        """ort_scene_create_from_lists: no octree needed; `lists` is a ShapeLists (HostScene.lists()).
+        build_on_device: True / False / None = by scene size (ORT_BUILD_AUTO)"""
         self = cls.__new__(cls)
         self.L = library or lib()
         h = vp(0)
-        _check(self.L.ort_scene_create_from_lists(_as_ptr(world_ptr), C.byref(lists), device,
-                                                  ORT_BUILD_ON_DEVICE if build_on_device else 0, C.byref(h)), self.L)
+        flags = ORT_BUILD_AUTO if build_on_device is None else (ORT_BUILD_ON_DEVICE if build_on_device else 0)
+        _check(self.L.ort_scene_create_from_lists(_as_ptr(world_ptr), C.byref(lists), device, flags, C.byref(h)), self.L)
         self.h = h
         self.device = device
         return self

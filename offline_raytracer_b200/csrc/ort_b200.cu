@@ -495,8 +495,10 @@ static double seconds_since(std::chrono::steady_clock::time_point t0)
 
 int ort_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, OrtScene **scene_out)
 {
-    uint32_t flags = 0;
-    if(const char *e = getenv("ORT_BVH_BUILD")) if(!strcmp(e, "device")) flags |= ORT_BUILD_ON_DEVICE;
+    // ORT_BVH_BUILD = host | device; unset: the host's binned-SAH builder up to a million records (well
+    // under a second, slightly better trees), the CUDA builder beyond
+    uint32_t flags = ORT_BUILD_AUTO;
+    if(const char *e = getenv("ORT_BVH_BUILD")) flags = !strcmp(e, "device") ? ORT_BUILD_ON_DEVICE : 0u;
     return ort_scene_create_ex(world, top_most_node, device, flags, scene_out);
 }
 
@@ -512,11 +514,10 @@ static int create_scene_from_records(std::vector<HostPrim> &prims, FlatScene &fl
     if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_MERGE_SHAPES")) opt.merge_shapes = atoi(e) != 0;
-    const bool on_device = (flags & ORT_BUILD_ON_DEVICE) != 0u;
+    const bool on_device = (flags & ORT_BUILD_ON_DEVICE) != 0u || ((flags & ORT_BUILD_AUTO) != 0u && prims.size() >= ORT_BUILD_AUTO_RECORDS);
     bs.on_device = on_device ? 1u : 0u;
     build::DeviceBuildResult built; memset(&built, 0, sizeof(built));
     auto t0 = std::chrono::steady_clock::now();
-    t0 = std::chrono::steady_clock::now();
     if(on_device)
     {
         // Morton sort, PLOC clustering and the collapse to 8-wide run as CUDA kernels
@@ -632,10 +633,16 @@ int ort_scene_create_from_lists(const OrtWorld *world, const OrtShapeLists *list
     std::string err;
     OrtBuildStats bs; memset(&bs, 0, sizeof(bs));
     auto t0 = std::chrono::steady_clock::now();
+    if(!world || !lists) return fail(ORT_ERR_ARG, "null world / shape lists");
+    if(flags & ORT_BUILD_AUTO)
+    {
+        uint64_t records = (uint64_t)lists->cylinder_count + lists->box_count + lists->sphere_count;
+        for(uint32_t m = 0; m < lists->mesh_count; ++m) records += lists->meshes[m].index_count / 3u;
+        if(records >= ORT_BUILD_AUTO_RECORDS) flags |= ORT_BUILD_ON_DEVICE;
+    }
     if(flags & ORT_BUILD_ON_DEVICE)
     {
         // records, ranks and the tree all on the device: the host touches the meshes only to copy them
-        if(!world || !lists) return fail(ORT_ERR_ARG, "null world / shape lists");
         BuildOptions opt;
         if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
         if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
