@@ -177,10 +177,13 @@ def test_padding_is_what_makes_culling_safe(sim, testscene_host, testscene_oracl
     assert np.array_equal(a["rank"], b["rank"])
 
 
-def test_parallel_builder_gives_the_same_hits_with_comparable_work(sim, testscene_host, testscene_oracle):
+@pytest.mark.parametrize("top", ["default", "0"])
+def test_parallel_builder_gives_the_same_hits_with_comparable_work(sim, testscene_host, testscene_oracle, top, monkeypatch):
     """the data-parallel builder (csrc/bvh_build.h: Morton order, PLOC clustering,
     level-by-level collapse to 8-wide), executed on the host, yields a tree that returns the same
     (t, rank, material, normal) for every ray as the binned-SAH tree, at a comparable traversal cost"""
+    if top != "default":
+        monkeypatch.setenv("ORT_PLOC_TOP", top)          # pure clustering, no SAH-built top
     hs, osc = testscene_host, testscene_oracle
     L = sim.L
     L.sim_scene_create_parallel.restype = vp
