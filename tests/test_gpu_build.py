@@ -80,11 +80,18 @@ def test_device_built_scene_gives_identical_hits_and_images(ort, testscene_host,
     a.close(); b.close()
 
 
-def test_scene_from_shape_lists_on_the_device(ort, testscene_host, tmp_path):
-    """no octree anywhere: lists -> ranks by sorting -> device build; same hits, same image"""
-    hs = testscene_host
+@pytest.mark.parametrize("scene", ["testscene", "box_spheres", "c4_dwarf_hdr"])
+def test_scene_from_shape_lists_on_the_device(ort, scene):
+    """no octree anywhere: lists -> ranks by sorting -> records -> tree, all on the device; same ranks,
+    same octree statistics, same hits, same image as the octree hand-off with the host builder
+    (box_spheres has no mesh at all, c4 an .obj mesh)"""
+    base = ol.SCENES_DIR if scene == "box_spheres" else ol.DATA_DIR
+    path = os.path.join(ol.DATA_DIR, "testscene.scn") if scene == "testscene" else os.path.join(ol.SCENES_DIR, scene + ".scn")
+    Wd, Hd = 160, 90
+    hs = ort.HostScene.load(path, base, Wd, Hd)
     a = ort.Scene(hs.world, hs.root, 0, build_on_device=False)
-    hs2 = ort.HostScene.load(os.path.join(ol.DATA_DIR, "testscene.scn"), ol.DATA_DIR, hs.width, hs.height, octree=False)
+    hs2 = ort.HostScene.load(path, base, Wd, Hd, octree=False)
+    assert not hs2.root
     b = ort.Scene.from_lists(hs2.world, hs2.lists(), 0, build_on_device=True)
     ia, ib = a.info(), b.info()
     for k in ("triangle_count", "sphere_count", "box_count", "cylinder_count", "csg_count", "record_count",
@@ -97,13 +104,13 @@ def test_scene_from_shape_lists_on_the_device(ort, testscene_host, tmp_path):
     # (a cylinder's aux index, bits 8.. of the kind word, depends on the order of emission)
     pa[:, 11] &= 0xFF; pb[:, 11] &= 0xFF
     assert np.array_equal(pa, pb)
-    st = b.build_stats()
-    assert st["on_device"] == 1 and st["ploc_iterations"] > 5
-    o, d = ol.make_incoherent_rays(300000, [-2.9, -2.9, 0.0], [14.9, 14.9, 8.8])
+    assert b.build_stats()["on_device"] == 1
+    lo, hi = np.array(ia["root_min"]) + 0.05, np.array(ia["root_max"]) - 0.05
+    o, d = ol.make_incoherent_rays(200000, list(lo), list(hi))
     ra, rb = a.raycast_batch(o, d), b.raycast_batch(o, d)
     assert np.array_equal(ra["rank"], rb["rank"]) and np.array_equal(bits(ra["t"]), bits(rb["t"]))
     assert np.array_equal(ra["mat"], rb["mat"]) and np.array_equal(bits(ra["normal"]), bits(rb["normal"]))
-    P = ort.default_params(160, 90, 4, chunk_spp=2, kernel=ort.ORT_KERNEL_WAVEFRONT)
+    P = ort.default_params(Wd, Hd, 4, chunk_spp=2, kernel=ort.ORT_KERNEL_WAVEFRONT)
     ia_, _ = a.render(hs.camera, P)
     ib_, _ = b.render(hs2.camera, P)
     assert np.array_equal(bits(ia_), bits(ib_))
