@@ -51,6 +51,16 @@ if os.environ.get("ORT_BENCH_CONFIG", "") == "c4":
     SCENE = os.path.join(ROOT, "scenes", "c4_dwarf_hdr.scn")
     SCENE_NAME, SCALING = "scenes/c4_dwarf_hdr.scn", "strong"
     WORKLOAD = "C4 dwarf.obj in closed room, emitters > 1, 3840x2160, 1024 spp in total (%d per GPU), rr 0.8" % SPP_PER_GPU
+# ORT_BENCH_CONFIG=c5: BASELINE config 5 -- 729 baked bunnies = 50.6 M triangles in a closed room
+# (tools/make_scene_grid.py 27 <file>, path in ORT_BENCH_C5_SCENE), 3840x2160, 512 spp in total; the scene is
+# handed over as shape lists and ranks, records and BVH are built on the device
+FROM_LISTS = False
+if os.environ.get("ORT_BENCH_CONFIG", "") == "c5":
+    WIDTH, HEIGHT = 3840, 2160
+    SPP_PER_GPU = max(CHUNK_SPP, 512 // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
+    SCENE = os.environ.get("ORT_BENCH_C5_SCENE", "/tmp/c5_729.scn")
+    SCENE_NAME, SCALING, FROM_LISTS = "tools/make_scene_grid.py 27", "strong", True
+    WORKLOAD = "C5 729 bunnies = 50.6 M triangles in closed room, 3840x2160, 512 spp in total (%d per GPU), rr 0.8" % SPP_PER_GPU
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -209,8 +219,8 @@ def main_gpu(args):
 
     if not os.path.exists(os.path.join(DATA_DIR, "bunny.ply")):
         raise SystemExit("bench.py: %s/bunny.ply is not staged; run __graft_entry__.build() where /root/reference exists" % DATA_DIR)
-    hs = ort.HostScene.load(SCENE, DATA_DIR, WIDTH, HEIGHT)
-    scene = ort.Scene(hs.world, hs.root, local)
+    hs = ort.HostScene.load(SCENE, DATA_DIR, WIDTH, HEIGHT, octree=not FROM_LISTS)
+    scene = ort.Scene.from_lists(hs.world, hs.lists(), local) if FROM_LISTS else ort.Scene(hs.world, hs.root, local)
     info = scene.info()
 
     spp_total = SPP_PER_GPU * world
@@ -304,7 +314,8 @@ def main_gpu(args):
     if os.path.exists(cpath):
         try:
             CL = ort.lib(cpath)
-            cs = ort.Scene(hs.world, hs.root, local, library=CL)
+            cs = (ort.Scene.from_lists(hs.world, hs.lists(), local, library=CL) if FROM_LISTS
+                  else ort.Scene(hs.world, hs.root, local, library=CL))
             Pc = ort.default_params(WIDTH, HEIGHT, CHUNK_SPP, rr=RR, seed=SEED, chunk_spp=CHUNK_SPP)
             _, cst = cs.render(hs.camera, Pc)
             per_ray = {"node_visits": cst["node_visits"] / cst["rays"], "box_tests": cst["box_tests"] / cst["rays"],
@@ -352,7 +363,8 @@ def main_gpu(args):
                          "peak_source": "measured in this run: FMUL+FADD chain kernel (no FMA), ort_measure_fp32_peak",
                          "algorithmic_flops_per_ray": flops_per_ray}
 
-    kind, threads, out = run_reference_subprocess(1, 0, args.sample_spp) if world == 1 else (None, 0, None)
+    # (config 5 exceeds the reference's own limits -- 99 meshes, fixed arenas -- so it has no CPU arm)
+    kind, threads, out = run_reference_subprocess(1, 0, args.sample_spp) if world == 1 and not FROM_LISTS else (None, 0, None)
     cpu_baseline = cpu_baseline_object(kind, threads, out, args.sample_spp, 1) if out else None
 
     emit({"metric": "path_samples_per_second", "value": value, "unit": "Msamples/s", "n_gpus": world,
