@@ -19,6 +19,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <string>
+#include <utility>
 
 #include "core_math.h"
 
@@ -314,11 +317,28 @@ int assemble_scene(const char *scn_path, const char *base_dir, int32_t width, in
     hs->meshes.assign(nm, OrtMesh());
     hs->mesh_vertices.assign(nm, std::vector<ort_v3>());
     hs->mesh_indices.assign(nm, std::vector<uint32_t>());
+    std::map<std::string, size_t> parsed_as;
+    std::vector<std::pair<std::vector<ort_v3>, std::vector<uint32_t> > > pristine;      // as parsed, before the bake
     for(size_t mi = 0; mi < nm; ++mi)
     {
         const ParsedMesh &info = sc.meshes[mi];
-        rc = load_mesh_file(info.file_path.c_str(), &hs->mesh_vertices[mi], &hs->mesh_indices[mi], err);
-        if(rc != ORT_OK) return rc;
+        // the reference re-parses the file for every `mesh` line (macos_main.mm:344-381); parsing is a
+        // pure function of the file, so a file seen before is copied instead (config 5 names bunny.ply 729 times)
+        {
+            std::map<std::string, size_t>::const_iterator seen = parsed_as.find(info.file_path);
+            if(seen == parsed_as.end())
+            {
+                rc = load_mesh_file(info.file_path.c_str(), &hs->mesh_vertices[mi], &hs->mesh_indices[mi], err);
+                if(rc != ORT_OK) return rc;
+                parsed_as[info.file_path] = pristine.size();
+                pristine.push_back(std::make_pair(hs->mesh_vertices[mi], hs->mesh_indices[mi]));
+            }
+            else
+            {
+                hs->mesh_vertices[mi] = pristine[seen->second].first;
+                hs->mesh_indices[mi] = pristine[seen->second].second;
+            }
+        }
         OrtMesh &mesh = hs->meshes[mi];
         memset(&mesh, 0, sizeof(mesh));
         mesh.vertices = hs->mesh_vertices[mi].data();
