@@ -170,3 +170,15 @@ def test_hdr_writer_reproduces_showcase_bytes(ort, tmp_path):
     canonical = (b[..., :3].max(-1) >= 128) & (b[..., :3].max(-1) <= 254)
     assert canonical.mean() > 0.99
     assert np.array_equal(a[canonical], b[canonical])
+
+
+def test_abi_headers_compile_as_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/ort_b200.h (and ort_scene.h) must be valid C99 on their own"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ort_b200.h"\n'
+                   'int main(void) { OrtShapeLists l; OrtBuildStats b; OrtRenderParams p; OrtRenderStats s;\n'
+                   '  (void)l; (void)b; (void)p; (void)s; return ort_stream_seed(1u, 2u, 3u) == 0u; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I" + os.path.join(ol.ROOT, "include"), str(src)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
