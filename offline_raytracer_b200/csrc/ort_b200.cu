@@ -520,6 +520,8 @@ static int create_scene_from_records(std::vector<HostPrim> &prims, FlatScene &fl
     if(const char *e = getenv("ORT_BVH_TRAVERSAL_COST")) opt.traversal_cost = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_PAD_REL")) opt.pad_rel = (float)atof(e);
     if(const char *e = getenv("ORT_BVH_MERGE_SHAPES")) opt.merge_shapes = atoi(e) != 0;
+    if(const char *e = getenv("ORT_BVH_OPTIMAL")) opt.optimal_collapse = atoi(e) != 0;
+    if(const char *e = getenv("ORT_BVH_NODE_COST")) opt.wide_node_cost = (float)atof(e);
     const bool on_device = (flags & ORT_BUILD_ON_DEVICE) != 0u || ((flags & ORT_BUILD_AUTO) != 0u && prims.size() >= ORT_BUILD_AUTO_RECORDS);
     bs.on_device = on_device ? 1u : 0u;
     build::DeviceBuildResult built; memset(&built, 0, sizeof(built));

@@ -266,6 +266,7 @@ struct B2Node
     Box box;
     uint32_t left, right;     // children (inner)
     uint32_t first, count;    // leaf range in the index permutation (count > 0 = leaf)
+    uint32_t span;            // primitives below the node: idx[first .. first + span)
 };
 
 struct Builder
@@ -292,7 +293,7 @@ struct Builder
             cbox.grow_pt(&cen[3 * idx[i]]);
         }
         B2Node &nd = nodes[job.node];
-        nd.box = box; nd.left = nd.right = 0; nd.first = job.first; nd.count = job.count;
+        nd.box = box; nd.left = nd.right = 0; nd.first = job.first; nd.count = job.count; nd.span = job.count;
         if(job.count <= 1) return false;
 
         double best_cost = 1e300; int best_axis = -1, best_bin = -1;
@@ -492,10 +493,59 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
 
     const bool timing = getenv("ORT_TIMING") != 0;
     auto t0 = std::chrono::steady_clock::now();
-    Builder b(prims, opt);
+    // With the optimal collapse the binary tree is built down to single primitives and the
+    // dynamic programme below decides which subtrees become leaves.
+    BuildOptions bopt = opt;
+    if(opt.optimal_collapse) bopt.max_leaf = 1;
+    Builder b(prims, bopt);
     b.build();
     auto t1 = std::chrono::steady_clock::now();
     if(timing) fprintf(stderr, "[ort] binned-SAH build of %zu records: %.2f s\n", prims.size(), std::chrono::duration<double>(t1 - t0).count());
+
+    // Optimal collapse to 8-wide (Ylitie, Karras, Laine 2017, section 3): C(n, i) = least SAH cost of
+    // representing binary subtree n with at most i child slots of a wide node,
+    //   C(n, 1)     = min( A_n * P_n          [a leaf of P_n <= max_leaf primitives],
+    //                      A_n * c_node + D(n, 8)  [a wide node of its own] )
+    //   C(n, i > 1) = min( D(n, i), C(n, i - 1) ),   D(n, j) = min_{0<k<j} C(left, k) + C(right, j - k)
+    // evaluated bottom-up (children carry larger indices than their parent); the emission below follows
+    // the minimising choices instead of greedily opening the largest child.
+    const size_t NB = b.nodes.size();
+    std::vector<float> C;            // C[8 * n + i], i = 1..7
+    std::vector<uint8_t> as_leaf, dist_k;     // dist_k[9 * n + j], j = 2..8
+    if(opt.optimal_collapse)
+    {
+        C.assign(8 * NB, 0.f); as_leaf.assign(NB, 0); dist_k.assign(9 * NB, 0);
+        const double c_node = opt.wide_node_cost;
+        for(size_t n = NB; n-- > 0; )
+        {
+            const B2Node &nd = b.nodes[n];
+            const double A = nd.box.area(), P = (double)nd.span;
+            if(nd.count > 0)
+            {
+                for(int i = 1; i <= 7; ++i) C[8 * n + i] = (float)(A * P);
+                as_leaf[n] = 1;
+                continue;
+            }
+            double D[9];
+            for(int j = 2; j <= 8; ++j)
+            {
+                double best = 1e300; int bk = 1;
+                for(int k = 1; k < j; ++k)
+                {
+                    int kl = k > 7 ? 7 : k, kr = (j - k) > 7 ? 7 : (j - k);
+                    double v = (double)C[8 * nd.left + kl] + (double)C[8 * nd.right + kr];
+                    if(v < best) { best = v; bk = k; }
+                }
+                D[j] = best; dist_k[9 * n + j] = (uint8_t)bk;
+            }
+            double c_leaf = nd.span <= opt.max_leaf ? A * P : 1e300;
+            double c_int = D[8] + A * c_node;
+            as_leaf[n] = c_leaf <= c_int ? 1 : 0;
+            C[8 * n + 1] = (float)std::min(c_leaf, c_int);
+            for(int i = 2; i <= 7; ++i) C[8 * n + i] = std::min((float)D[i], C[8 * n + i - 1]);
+        }
+    }
+    auto kid_is_leaf = [&](uint32_t id) { return opt.optimal_collapse ? as_leaf[id] != 0 : b.nodes[id].count > 0; };
 
     struct WItem { uint32_t b2; uint32_t depth; };
     std::deque<WItem> queue;
@@ -510,12 +560,30 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
         size_t self = next_out++;
         if(it.depth > wide_depth) wide_depth = it.depth;
 
-        // gather up to 8 children by repeatedly opening the largest inner child
+        // gather up to 8 children: by the dynamic programme's choices, or by repeatedly opening the largest inner child
         uint32_t kids[8]; int nk = 0;
         const B2Node &rootn = b.nodes[it.b2];
-        if(rootn.count > 0) { kids[nk++] = it.b2; }             // degenerate: the whole (sub)tree is one leaf
+        if(kid_is_leaf(it.b2)) { kids[nk++] = it.b2; }          // degenerate: the whole (sub)tree is one leaf
+        else if(opt.optimal_collapse)
+        {
+            struct Slot { uint32_t node; int budget; };
+            Slot stack[16]; int sp = 0;
+            int k = dist_k[9 * it.b2 + 8];
+            stack[sp++] = Slot{ rootn.right, 8 - k };
+            stack[sp++] = Slot{ rootn.left, k };
+            while(sp > 0)
+            {
+                Slot c = stack[--sp];
+                int i = c.budget > 7 ? 7 : c.budget;
+                while(i > 1 && C[8 * c.node + i] == C[8 * c.node + i - 1]) --i;
+                if(i == 1 || b.nodes[c.node].count > 0) { kids[nk++] = c.node; continue; }
+                int kk = dist_k[9 * c.node + i];
+                stack[sp++] = Slot{ b.nodes[c.node].right, i - kk };
+                stack[sp++] = Slot{ b.nodes[c.node].left, kk };
+            }
+        }
         else { kids[nk++] = rootn.left; kids[nk++] = rootn.right; }
-        for(;;)
+        for(; !opt.optimal_collapse; )
         {
             if(nk >= 8) break;
             int pick = -1; double pa = -1.0;
@@ -598,7 +666,8 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
         {
             if(kid_at[s] < 0) continue;
             const B2Node &c = b.nodes[kids[kid_at[s]]];
-            if(c.count == 0)
+            const uint32_t c_count = kid_is_leaf(kids[kid_at[s]]) ? c.span : 0u;
+            if(c_count == 0)
             {
                 n.imask |= (uint8_t)(1u << s);
                 n.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
@@ -607,17 +676,17 @@ int emit_tree(const std::vector<HostPrim> &prims, const BuildOptions &opt, FlatS
             }
             else
             {
-                if(c.count > 3 || prim_off + c.count > 24) { *err = "internal: leaf too large"; return ORT_ERR_LIMIT; }
-                uint32_t unary = (1u << c.count) - 1u;
+                if(c_count > 3 || prim_off + c_count > 24) { *err = "internal: leaf too large"; return ORT_ERR_LIMIT; }
+                uint32_t unary = (1u << c_count) - 1u;
                 n.meta[s] = (uint8_t)((unary << 5) | prim_off);
-                for(uint32_t i = 0; i < c.count; ++i)
+                for(uint32_t i = 0; i < c_count; ++i)
                 {
                     const HostPrim &hp = prims[b.idx[c.first + i]];
                     if(hp.kind != PRIM_TRIANGLE) only_triangles = false;
                     PrimRec r = make_record(hp, out);
                     out->prims.push_back(r);
                 }
-                prim_off += c.count;
+                prim_off += c_count;
             }
         }
         if(n.prim_base >= ORT_NODE_MIXED_KINDS) { *err = "too many primitive records"; return ORT_ERR_LIMIT; }

@@ -25,6 +25,8 @@ void *sim_scene_create(const OrtWorld *world, const OrtBVHOctreeNode *root, floa
     if(traversal_cost > 0) opt.traversal_cost = traversal_cost;
     if(pad_rel >= 0) opt.pad_rel = pad_rel;
     if(pad_scene >= 0) opt.pad_scene = pad_scene;
+    if(const char *e = getenv("ORT_BVH_OPTIMAL")) opt.optimal_collapse = atoi(e) != 0;
+    if(const char *e = getenv("ORT_BVH_NODE_COST")) opt.wide_node_cost = (float)atof(e);
     std::string err;
     if(flatten_scene(world, root, opt, &s->flat, &err) != ORT_OK)
     {
