@@ -24,14 +24,14 @@ __global__ void k_morton(uint32_t n, const float *__restrict__ boxes, D3 lo, D3 
 }
 
 __global__ void k_init_leaves(uint32_t n, const uint32_t *__restrict__ order, const float *__restrict__ boxes,
-                              B2 *nodes, uint32_t *sizes, float *cost, uint32_t *cluster)
+                              B2 *nodes, uint32_t *sizes, Dp *cost, uint32_t *cluster)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
     B2 l; uint32_t src = order[i];
     for(int k = 0; k < 3; ++k) { l.lo[k] = boxes[6 * (size_t)src + k]; l.hi[k] = boxes[6 * (size_t)src + 3 + k]; }
     l.left = B2_LEAF; l.right = src;
-    nodes[i] = l; sizes[i] = 1u | B2_LEAF_FLAG; cost[i] = (float)half_area(l); cluster[i] = i;
+    nodes[i] = l; sizes[i] = 1u | B2_LEAF_FLAG; dp_leaf(&cost[i], half_area(l)); cluster[i] = i;
 }
 
 __global__ void k_ploc_nearest(uint32_t n, const uint32_t *__restrict__ cluster, const B2 *__restrict__ nodes, uint32_t radius, uint32_t *nn)
@@ -50,7 +50,7 @@ __global__ void k_ploc_fate(uint32_t n, const uint32_t *__restrict__ nn, uint32_
 
 __global__ void k_ploc_apply(uint32_t n, const uint32_t *__restrict__ nn, const uint32_t *__restrict__ cluster,
                              const uint32_t *__restrict__ fate, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ mid,
-                             uint32_t next_node, B2 *nodes, uint32_t *sizes, float *cost, uint32_t *new_cluster,
+                             uint32_t next_node, B2 *nodes, uint32_t *sizes, Dp *cost, uint32_t *new_cluster,
                              uint32_t max_leaf, float traversal_cost)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +59,7 @@ __global__ void k_ploc_apply(uint32_t n, const uint32_t *__restrict__ nn, const 
 
 // the clusters still alive: their nodes, sizes and costs, packed for the host's top-tree build
 __global__ void k_pack_clusters(uint32_t count, const uint32_t *__restrict__ cluster, const B2 *__restrict__ nodes,
-                                const uint32_t *__restrict__ sizes, const float *__restrict__ cost, B2 *out_nodes, uint32_t *out_sizes, float *out_cost)
+                                const uint32_t *__restrict__ sizes, const Dp *__restrict__ cost, B2 *out_nodes, uint32_t *out_sizes, Dp *out_cost)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= count) return;
@@ -68,12 +68,12 @@ __global__ void k_pack_clusters(uint32_t count, const uint32_t *__restrict__ clu
 }
 
 __global__ void k_gather(uint32_t n_items, const Item *__restrict__ items, const B2 *__restrict__ nodes, const uint32_t *__restrict__ sizes,
-                         uint32_t max_leaf, Kids *kids, uint32_t *n_inner, uint32_t *n_prims)
+                         const Dp *__restrict__ cost, uint32_t max_leaf, Kids *kids, uint32_t *n_inner, uint32_t *n_prims)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_items) return;
     Kids k;
-    gather_kids(items[i].b2, nodes, sizes, max_leaf, &k);
+    gather_kids(items[i].b2, nodes, sizes, cost, max_leaf, &k);
     kids[i] = k; n_inner[i] = k.n_inner; n_prims[i] = k.n_prims;
 }
 
@@ -121,7 +121,7 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
 
     float *d_boxes = 0; PrimRec *d_recs = 0;
     uint64_t *d_codes = 0, *d_codes2 = 0; uint32_t *d_idx = 0, *d_order = 0;
-    B2 *d_b2 = 0; uint32_t *d_sizes = 0; float *d_cost = 0;
+    B2 *d_b2 = 0; uint32_t *d_sizes = 0; Dp *d_cost = 0;
     uint32_t *d_cluster = 0, *d_cluster2 = 0, *d_nn = 0, *d_fate = 0, *d_keep = 0, *d_merge = 0, *d_pos = 0, *d_mid = 0;
     WideNode *d_wide = 0; Item *d_items = 0, *d_items2 = 0; Kids *d_kids = 0;
     void *d_temp = 0; size_t temp_bytes = 0;
@@ -158,7 +158,7 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
         BUILD_TRY(cudaMalloc((void **)&d_codes, (size_t)n * 8)); BUILD_TRY(cudaMalloc((void **)&d_codes2, (size_t)n * 8));
         BUILD_TRY(cudaMalloc((void **)&d_idx, (size_t)n * 4)); BUILD_TRY(cudaMalloc((void **)&d_order, (size_t)n * 4));
         BUILD_TRY(cudaMalloc((void **)&d_b2, (size_t)n * 2 * sizeof(B2)));
-        BUILD_TRY(cudaMalloc((void **)&d_sizes, (size_t)n * 2 * 4)); BUILD_TRY(cudaMalloc((void **)&d_cost, (size_t)n * 2 * 4));
+        BUILD_TRY(cudaMalloc((void **)&d_sizes, (size_t)n * 2 * 4)); BUILD_TRY(cudaMalloc((void **)&d_cost, (size_t)n * 2 * sizeof(Dp)));
         BUILD_TRY(cudaMalloc((void **)&d_cluster, (size_t)n * 4)); BUILD_TRY(cudaMalloc((void **)&d_cluster2, (size_t)n * 4));
         BUILD_TRY(cudaMalloc((void **)&d_nn, (size_t)n * 4)); BUILD_TRY(cudaMalloc((void **)&d_fate, (size_t)n * 4));
         BUILD_TRY(cudaMalloc((void **)&d_keep, (size_t)n * 4)); BUILD_TRY(cudaMalloc((void **)&d_merge, (size_t)n * 4));
@@ -197,7 +197,7 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
                 tb = temp_bytes;
                 BUILD_TRY(cub::DeviceScan::ExclusiveSum(d_temp, tb, d_merge, d_mid, (int)count));
                 k_ploc_apply<<<G(count), T>>>(count, d_nn, d_cluster, d_fate, d_pos, d_mid, next_node, d_b2, d_sizes, d_cost, d_cluster2,
-                                               in.max_leaf, in.traversal_cost);
+                                               in.max_leaf, in.node_cost);
                 uint32_t last[4];
                 BUILD_TRY(cudaMemcpy(&last[0], d_pos + (count - 1), 4, cudaMemcpyDeviceToHost));
                 BUILD_TRY(cudaMemcpy(&last[1], d_keep + (count - 1), 4, cudaMemcpyDeviceToHost));
@@ -212,19 +212,19 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
             if(count > 1)
             {
                 // the top of the tree: binned SAH over the remaining clusters, on the host (scene_flatten.cpp)
-                std::vector<B2> hn(2 * (size_t)count); std::vector<uint32_t> hs(2 * (size_t)count, 0u), hc(count); std::vector<float> hcost(2 * (size_t)count, 0.f);
+                std::vector<B2> hn(2 * (size_t)count); std::vector<uint32_t> hs(2 * (size_t)count, 0u), hc(count); std::vector<Dp> hcost(2 * (size_t)count);
                 B2 *d_pn = (B2 *)d_kids;                                   // scratch: the collapse has not started yet
-                uint32_t *d_ps = d_keep; float *d_pc = (float *)d_merge;
+                uint32_t *d_ps = d_keep; Dp *d_pc = (Dp *)d_items;          // scratch (count <= 65536 entries)
                 k_pack_clusters<<<G(count), T>>>(count, d_cluster, d_b2, d_sizes, d_cost, d_pn, d_ps, d_pc);
                 BUILD_TRY(cudaMemcpy(hn.data(), d_pn, (size_t)count * sizeof(B2), cudaMemcpyDeviceToHost));
                 BUILD_TRY(cudaMemcpy(hs.data(), d_ps, (size_t)count * 4, cudaMemcpyDeviceToHost));
-                BUILD_TRY(cudaMemcpy(hcost.data(), d_pc, (size_t)count * 4, cudaMemcpyDeviceToHost));
+                BUILD_TRY(cudaMemcpy(hcost.data(), d_pc, (size_t)count * sizeof(Dp), cudaMemcpyDeviceToHost));
                 BUILD_TRY(cudaMemcpy(hc.data(), d_cluster, (size_t)count * 4, cudaMemcpyDeviceToHost));
                 std::vector<uint32_t> local(count);
                 for(uint32_t c = 0; c < count; ++c) local[c] = c;
                 uint32_t local_next = count, local_root = 0;
                 BuildOptions o; o.traversal_cost = in.traversal_cost; o.max_leaf = in.max_leaf;
-                if(build_top_tree(local, o, in.max_leaf, in.traversal_cost, hn.data(), hs.data(), hcost.data(), &local_next, &local_root, err) != ORT_OK)
+                if(build_top_tree(local, o, in.max_leaf, in.node_cost, hn.data(), hs.data(), hcost.data(), &local_next, &local_root, err) != ORT_OK)
                 { ok = false; goto done; }
                 // local ids -> global ids: clusters keep theirs, new nodes follow next_node
                 auto global_id = [&](uint32_t l) { return l < count ? hc[l] : next_node + (l - count); };
@@ -232,7 +232,7 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
                 for(uint32_t j = count; j < local_next; ++j) { hn[j].left = global_id(hn[j].left); hn[j].right = global_id(hn[j].right); }
                 BUILD_TRY(cudaMemcpy(d_b2 + next_node, hn.data() + count, (size_t)added * sizeof(B2), cudaMemcpyHostToDevice));
                 BUILD_TRY(cudaMemcpy(d_sizes + next_node, hs.data() + count, (size_t)added * 4, cudaMemcpyHostToDevice));
-                BUILD_TRY(cudaMemcpy(d_cost + next_node, hcost.data() + count, (size_t)added * 4, cudaMemcpyHostToDevice));
+                BUILD_TRY(cudaMemcpy(d_cost + next_node, hcost.data() + count, (size_t)added * sizeof(Dp), cudaMemcpyHostToDevice));
                 uint32_t root_global = global_id(local_root);
                 BUILD_TRY(cudaMemcpy(d_cluster, &root_global, 4, cudaMemcpyHostToDevice));
                 next_node += added; count = 1;
@@ -252,7 +252,7 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
             {
                 ++depth;
                 if(n_items > wide_cap || node_count - node_offset > wide_cap) { *err = "internal: wide node bound exceeded"; ok = false; goto done; }
-                k_gather<<<G(n_items), T>>>(n_items, d_items, d_b2, d_sizes, in.max_leaf, d_kids, d_ninner, d_nprims);
+                k_gather<<<G(n_items), T>>>(n_items, d_items, d_b2, d_sizes, d_cost, in.max_leaf, d_kids, d_ninner, d_nprims);
                 size_t tb = temp_bytes;
                 BUILD_TRY(cub::DeviceScan::ExclusiveSum(d_temp, tb, d_ninner, d_ioff, (int)n_items));
                 tb = temp_bytes;
@@ -596,7 +596,7 @@ inline bool records_from_lists_on_device(const OrtWorld *world, const OrtShapeLi
         in->sphere_depth = 0;
         if(!spheres.empty() && emit_tree_public(spheres, o, flat, &in->sphere_depth, err) != ORT_OK) { ok = false; goto done; }
         flat->main_root = flat->tri_root = (uint32_t)flat->nodes.size();
-        in->max_leaf = o.max_leaf; in->traversal_cost = o.traversal_cost;
+        in->max_leaf = o.max_leaf; in->traversal_cost = o.traversal_cost; in->node_cost = o.wide_node_cost;
     }
     n_rest = n_tri + (uint32_t)none.size();          // merge_shapes: boxes and cylinders come back in `none` (the "tris" list)
     BUILD_TRY2(cudaMalloc((void **)&out->d_boxes, (size_t)(n_rest + 1) * 6 * sizeof(float)));

@@ -13,8 +13,9 @@
 //      a spatial-median LBVH; its weak spot is the top -- it only ever looks at Morton neighbours --
 //      so the last clusters are joined top-down by the host's binned-SAH builder (a few thousand
 //      boxes, milliseconds): node visits per ray on the 4.4 M-triangle grid 9.76 -> 9.13 (SAH 8.73).
-//   3. Collapse to 8-wide, level by level: each wide node opens its largest inner binary child until
-//      it has 8; binary subtrees of <= max_leaf primitives become leaf children.  Children are
+//   3. Collapse to 8-wide, level by level, following the optimal-collapse cost tables that were filled
+//      in as the binary nodes were created (which subtrees become leaves of <= max_leaf primitives,
+//      which share a wide node).  Children are
 //      assigned to octant slots, their boxes quantised outward to the node's 8-bit grid
 //      (bvh.h), and the level's child nodes / primitive records are placed by prefix sums, so the
 //      result is deterministic: the CUDA kernels (bvh_build.cuh) and the host loops over the same
@@ -153,13 +154,24 @@ ORT_HD uint32_t ploc_fate(uint32_t i, const uint32_t *nn)
 }
 
 // sizes[id] = primitives below node id, bit 31 = "this subtree is a leaf child": it holds <= max_leaf
-// primitives and testing them all whenever its box is hit costs no more (surface-area heuristic,
-// cost[] = SAH cost of the subtree's best form) than descending further
+// primitives and testing them all whenever its box is hit costs no more (surface-area heuristic, cost
+// tables below) than giving it a wide node of its own
 #define B2_LEAF_FLAG 0x80000000u
 ORT_HD uint32_t subtree_size(const uint32_t *sizes, uint32_t id) { return sizes[id] & ~B2_LEAF_FLAG; }
 
-// binary node `id` = parent of l and r: box, size, SAH cost and the leaf decision
-ORT_HD void merge_nodes(uint32_t id, uint32_t l, uint32_t r, B2 *nodes, uint32_t *sizes, float *cost, uint32_t max_leaf, float traversal_cost)
+// Optimal collapse to 8-wide (Ylitie, Karras, Laine 2017, section 3), evaluated bottom-up as the binary
+// nodes are created: C[i] = least SAH cost of representing the subtree with at most i child slots of a
+// wide node,
+//   C[1]     = min( A * P  [a leaf of P <= max_leaf primitives],  A * c_node + D(8)  [a wide node of its own] )
+//   C[i > 1] = min( D(i), C[i - 1] ),    D(j) = min_{0<k<j} C_left[k] + C_right[j - k],   k[j] = the minimising k
+struct Dp { float C[8]; uint8_t k[8]; };           // C[1..7]; k[j - 1] for j = 2..8
+ORT_HD void dp_leaf(Dp *d, double area)
+{
+    for(int i = 0; i < 8; ++i) { d->C[i] = (float)area; d->k[i] = 0; }
+}
+
+// binary node `id` = parent of l and r: box, size, the cost table and the leaf decision
+ORT_HD void merge_nodes(uint32_t id, uint32_t l, uint32_t r, B2 *nodes, uint32_t *sizes, Dp *cost, uint32_t max_leaf, float node_cost)
 {
     B2 a = nodes[l], b = nodes[r], m;
     for(int k = 0; k < 3; ++k)
@@ -171,16 +183,35 @@ ORT_HD void merge_nodes(uint32_t id, uint32_t l, uint32_t r, B2 *nodes, uint32_t
     nodes[id] = m;
     uint32_t count = subtree_size(sizes, l) + subtree_size(sizes, r);
     double area = half_area(m);
-    double as_leaf = area * (double)count, as_inner = (double)traversal_cost * area + (double)cost[l] + (double)cost[r];
-    bool leaf = count <= max_leaf && as_leaf <= as_inner;
+    const Dp cl = cost[l], cr = cost[r];
+    Dp d;
+    double D[9];
+    d.k[0] = 0;
+    for(int j = 2; j <= 8; ++j)
+    {
+        double best = 1e300; int bk = 1;
+        for(int k = 1; k < j; ++k)
+        {
+            int kl = k > 7 ? 7 : k, kr = (j - k) > 7 ? 7 : (j - k);
+            double v = (double)cl.C[kl] + (double)cr.C[kr];
+            if(v < best) { best = v; bk = k; }
+        }
+        D[j] = best; d.k[j - 1] = (uint8_t)bk;
+    }
+    double as_leaf = count <= max_leaf ? area * (double)count : 1e300;
+    double as_inner = (double)node_cost * area + D[8];
+    bool leaf = as_leaf <= as_inner;
     sizes[id] = count | (leaf ? B2_LEAF_FLAG : 0u);
-    cost[id] = (float)(leaf ? as_leaf : as_inner);
+    d.C[0] = 0.f;
+    d.C[1] = (float)(leaf ? as_leaf : as_inner);
+    for(int i = 2; i <= 7; ++i) { float di = (float)D[i]; d.C[i] = di < d.C[i - 1] ? di : d.C[i - 1]; }
+    cost[id] = d;
 }
 
 // writes the new cluster entry of i (pos = its index in the compacted list, mid = how many merges
 // precede it)
 ORT_HD void ploc_apply(uint32_t i, const uint32_t *nn, const uint32_t *cluster, uint32_t fate, uint32_t pos, uint32_t mid,
-                       uint32_t next_node, B2 *nodes, uint32_t *sizes, float *cost, uint32_t *new_cluster,
+                       uint32_t next_node, B2 *nodes, uint32_t *sizes, Dp *cost, uint32_t *new_cluster,
                        uint32_t max_leaf, float traversal_cost)
 {
     if(fate == 0u) return;
@@ -194,27 +225,29 @@ ORT_HD void ploc_apply(uint32_t i, const uint32_t *nn, const uint32_t *cluster, 
 // ---- 3. collapse to 8-wide -------------------------------------------------------------------------
 ORT_HD bool is_leaf_child(uint32_t id, const uint32_t *sizes, uint32_t max_leaf) { (void)max_leaf; return (sizes[id] & B2_LEAF_FLAG) != 0u; }
 
-// children of the wide node made from binary subtree `root`: open the largest inner child until 8
-ORT_HD void gather_kids(uint32_t root, const B2 *nodes, const uint32_t *sizes, uint32_t max_leaf, Kids *out)
+// children of the wide node made from binary subtree `root`: the subtrees the cost tables chose to share it
+ORT_HD void gather_kids(uint32_t root, const B2 *nodes, const uint32_t *sizes, const Dp *cost, uint32_t max_leaf, Kids *out)
 {
     uint32_t *kids = out->id;
     uint32_t nk = 0;
     if(is_leaf_child(root, sizes, max_leaf)) kids[nk++] = root;      // degenerate: the whole tree is one leaf
-    else { kids[nk++] = nodes[root].left; kids[nk++] = nodes[root].right; }
-    for(;;)
+    else
     {
-        if(nk >= 8u) break;
-        int pick = -1; double pa = -1.0;
-        for(uint32_t i = 0; i < nk; ++i)
-            if(!is_leaf_child(kids[i], sizes, max_leaf))
-            {
-                double a = half_area(nodes[kids[i]]);
-                if(a > pa) { pa = a; pick = (int)i; }
-            }
-        if(pick < 0) break;
-        uint32_t open = kids[pick];
-        kids[pick] = nodes[open].left;
-        kids[nk++] = nodes[open].right;
+        uint32_t st_node[16]; int st_budget[16]; int sp = 0;
+        int k = cost[root].k[7];
+        st_node[sp] = nodes[root].right; st_budget[sp++] = 8 - k;
+        st_node[sp] = nodes[root].left; st_budget[sp++] = k;
+        while(sp > 0)
+        {
+            --sp;
+            uint32_t c = st_node[sp]; int i = st_budget[sp] > 7 ? 7 : st_budget[sp];
+            const Dp dc = cost[c];
+            while(i > 1 && dc.C[i] == dc.C[i - 1]) --i;
+            if(i == 1 || nodes[c].left == B2_LEAF) { kids[nk++] = c; continue; }
+            int kk = dc.k[i - 1];
+            st_node[sp] = nodes[c].right; st_budget[sp++] = i - kk;
+            st_node[sp] = nodes[c].left; st_budget[sp++] = kk;
+        }
     }
     out->nk = nk;
     out->n_inner = 0; out->n_prims = 0;

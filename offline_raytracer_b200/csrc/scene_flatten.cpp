@@ -1051,6 +1051,7 @@ int prepare_parallel_build(std::vector<HostPrim> &prims, const BuildOptions &opt
     out->main_root = out->tri_root = (uint32_t)out->nodes.size();
     in->max_leaf = o.max_leaf;
     in->traversal_cost = o.traversal_cost;
+    in->node_cost = o.wide_node_cost;
     in->boxes.resize(6 * rest.size());
     in->recs.resize(rest.size());
     double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
@@ -1083,8 +1084,8 @@ uint32_t parallel_top_clusters(uint32_t n)
     return std::min(k, n / 64u);          // clustering does the bulk of the work whatever the scene size
 }
 
-int build_top_tree(const std::vector<uint32_t> &clusters, const BuildOptions &opt, uint32_t max_leaf, float traversal_cost,
-                   build::B2 *nodes, uint32_t *sizes, float *cost, uint32_t *next_node, uint32_t *root_out, std::string *err)
+int build_top_tree(const std::vector<uint32_t> &clusters, const BuildOptions &opt, uint32_t max_leaf, float node_cost,
+                   build::B2 *nodes, uint32_t *sizes, build::Dp *cost, uint32_t *next_node, uint32_t *root_out, std::string *err)
 {
     std::vector<HostPrim> items(clusters.size());
     for(size_t c = 0; c < clusters.size(); ++c)
@@ -1109,7 +1110,7 @@ int build_top_tree(const std::vector<uint32_t> &clusters, const BuildOptions &op
         {
             if(nd.left <= i || nd.right <= i) { *err = "internal: top tree node order"; return ORT_ERR_LIMIT; }
             uint32_t id = (*next_node)++;
-            build::merge_nodes(id, id_of[nd.left], id_of[nd.right], nodes, sizes, cost, max_leaf, traversal_cost);
+            build::merge_nodes(id, id_of[nd.left], id_of[nd.right], nodes, sizes, cost, max_leaf, node_cost);
             id_of[i] = id;
         }
     }
@@ -1144,13 +1145,13 @@ int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOption
     // 2. PLOC
     std::vector<B2> nodes(2 * (size_t)n);
     std::vector<uint32_t> sizes(2 * (size_t)n, 0u), cluster(n), next_cluster(n), nn(n), fate(n);
-    std::vector<float> cost(2 * (size_t)n, 0.f);
+    std::vector<Dp> cost(2 * (size_t)n);
     for(uint32_t i = 0; i < n; ++i)
     {
         B2 l; uint32_t src = order[i];
         for(int k = 0; k < 3; ++k) { l.lo[k] = in.boxes[6 * src + k]; l.hi[k] = in.boxes[6 * src + 3 + k]; }
         l.left = B2_LEAF; l.right = src;
-        nodes[i] = l; sizes[i] = 1u | B2_LEAF_FLAG; cost[i] = (float)half_area(l); cluster[i] = i;
+        nodes[i] = l; sizes[i] = 1u | B2_LEAF_FLAG; dp_leaf(&cost[i], half_area(l)); cluster[i] = i;
     }
     uint32_t count = n, next_node = n;
     const uint32_t top_k = parallel_top_clusters(n);
@@ -1162,7 +1163,7 @@ int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOption
         for(uint32_t i = 0; i < count; ++i)
         {
             ploc_apply(i, nn.data(), cluster.data(), fate[i], pos, mid, next_node, nodes.data(), sizes.data(), cost.data(), next_cluster.data(),
-                       in.max_leaf, in.traversal_cost);
+                       in.max_leaf, in.node_cost);
             pos += fate[i] != 0u; mid += fate[i] == 2u;
         }
         next_node += mid; count = pos;
@@ -1172,7 +1173,7 @@ int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOption
     {
         uint32_t top_root = 0;
         std::vector<uint32_t> live(cluster.begin(), cluster.begin() + count);
-        rc = build_top_tree(live, opt, in.max_leaf, in.traversal_cost, nodes.data(), sizes.data(), cost.data(), &next_node, &top_root, err);
+        rc = build_top_tree(live, opt, in.max_leaf, in.node_cost, nodes.data(), sizes.data(), cost.data(), &next_node, &top_root, err);
         if(rc != ORT_OK) return rc;
         cluster[0] = top_root;
     }
@@ -1191,7 +1192,7 @@ int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOption
         uint32_t total_inner = 0, total_prims = 0;
         for(size_t i = 0; i < items.size(); ++i)
         {
-            gather_kids(items[i].b2, nodes.data(), sizes.data(), in.max_leaf, &kids[i]);
+            gather_kids(items[i].b2, nodes.data(), sizes.data(), cost.data(), in.max_leaf, &kids[i]);
             total_inner += kids[i].n_inner; total_prims += kids[i].n_prims;
         }
         out->nodes.resize(node_count + total_inner);

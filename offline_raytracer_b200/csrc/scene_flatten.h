@@ -85,6 +85,7 @@ struct ParallelBuildInput
     double scene_lo[3], scene_scale[3];   // box-centre bounds -> 21-bit grid
     uint32_t max_leaf;
     float traversal_cost;
+    float node_cost;                 // cost of a wide-node visit relative to a primitive test (optimal collapse)
     uint32_t sphere_depth;           // depth of the sphere tree already emitted into the FlatScene
 };
 int prepare_parallel_build(std::vector<HostPrim> &prims, const BuildOptions &opt, FlatScene *out, ParallelBuildInput *in, std::string *err);
@@ -92,9 +93,9 @@ int build_wide_bvh_parallel_host(std::vector<HostPrim> &prims, const BuildOption
 #define ORT_PLOC_RADIUS 16u
 #define ORT_PLOC_TOP_CLUSTERS 65536u     // the last so many clusters (at most n / 64) go to the SAH builder (ORT_PLOC_TOP overrides; 0 = none)
 uint32_t parallel_top_clusters(uint32_t n);
-namespace build { struct B2; }
-int build_top_tree(const std::vector<uint32_t> &clusters, const BuildOptions &opt, uint32_t max_leaf, float traversal_cost,
-                   build::B2 *nodes, uint32_t *sizes, float *cost, uint32_t *next_node, uint32_t *root_out, std::string *err);
+namespace build { struct B2; struct Dp; }
+int build_top_tree(const std::vector<uint32_t> &clusters, const BuildOptions &opt, uint32_t max_leaf, float node_cost,
+                   build::B2 *nodes, uint32_t *sizes, build::Dp *cost, uint32_t *next_node, uint32_t *root_out, std::string *err);
 // pieces of the host path the device execution (bvh_build.cuh) reuses for the few analytic shapes
 int collect_analytic(const OrtWorld *world, const OrtShapeLists *lists, f3 root_center, f3 root_half,
                      std::vector<HostPrim> *analytic, uint32_t *keys, std::string *err);
