@@ -553,7 +553,17 @@ static int create_scene_from_records(std::vector<HostPrim> &prims, FlatScene &fl
     }
     else
     {
+        // the optimal collapse can give a deeper tree than the greedy one; should that ever exceed the
+        // traversal stack (ORT_STACK_SIZE), fall back to the greedy collapse
+        std::vector<HostPrim> backup;
+        if(opt.optimal_collapse && prims.size() < 2000000u) backup = prims;
         rc = build_wide_bvh(prims, opt, &flat, &err);
+        if(rc == ORT_ERR_LIMIT && !backup.empty())
+        {
+            BuildOptions greedy = opt; greedy.optimal_collapse = false;
+            err.clear();
+            rc = build_wide_bvh(backup, greedy, &flat, &err);
+        }
         if(rc != ORT_OK) return fail(rc, err);
         bs.build_s = (float)seconds_since(t0);
     }
