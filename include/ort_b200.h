@@ -14,6 +14,16 @@
  *
  * There is NO CPU fallback: every render / raycast entry point fails with
  * ORT_ERR_CUDA when no CUDA device is usable.
+ *
+ * THREADS.  An OrtScene may be used from any number of host threads: every entry
+ * point that touches the handle's scratch (framebuffers, counters, path pools,
+ * streams) takes the handle's lock for the whole call, so concurrent calls on one
+ * handle are serialised -- which is what the GPU would do with them anyway.  This
+ * is what lets ort_tiled_raytrace_bvh sit inside the reference's thread callback,
+ * which nine workers run at once (code/macos_main.mm:150-163, 574-598); tiles of
+ * one image rendered that way are bit-identical to one whole-image call.  Handles
+ * on different devices run concurrently (one handle per GPU).  ort_last_error()
+ * is per thread.
  */
 #ifndef ORT_B200_H
 #define ORT_B200_H
@@ -56,6 +66,28 @@ int ort_measure_fp32_peak(int device, float *tflops_non_fma, float *reserved);
  * three quotients of math.h:235 `v3 / f32` as used by `normalize`, math.h:299) against the
  * compiler's IEEE-754 division on `triples` random operand sets; *mismatches must come back 0. */
 int ort_selftest_div3(int device, uint64_t triples, uint32_t seed, uint64_t *tested, uint64_t *mismatches);
+/* Measures the L2 roofline denominator of `device` ("the build must measure both"): GB/s of
+ * a kernel in which every block streams the same `buffer_mib` MiB buffer (0 = 32; it must stay inside the
+ * 126 MB L2) with L1-bypassing 128-bit loads -- the way a wide node that misses L1 is served. */
+int ort_measure_l2_bandwidth(int device, uint32_t buffer_mib, float *gb_per_s);
+
+/* ------------------------------------------------------------------------
+ * Device differential harness (tests).  Runs the DEVICE build of the intersectors
+ * (csrc/core_math.h; code/ray.cpp:63-352) and of the BSDF (csrc/path.h;
+ * code/ray.cpp:825-1161) -- the very functions the render kernels inline -- on
+ * explicit inputs, so that the reference's golden vectors are checked on the GPU.
+ *   kind 0 triangle: v0 v1 v2 o d (15 floats per case)     1 sphere: c r o d (10)
+ *        2 box: min max o d (12)                           3 cylinder: base axis r o d (13)
+ *   out: 5 floats per case = t (-1 = miss), unnormalised normal xyz, inner-hit flag
+ *        (IntersectionTestResult, ray.cpp:54-59).
+ * ort_selftest_bsdf: materials as 10 floats (Kd, Ks, Kt, ior); per case sample_brdf
+ * from `state` (-> wi, is_transmission, state after), pdf_brdf and eval_scattering
+ * of (N, wi, wo).  All pointers are HOST pointers.
+ * ---------------------------------------------------------------------- */
+int ort_selftest_intersect(int device, uint32_t kind, uint32_t n, const float *cases, float *out);
+int ort_selftest_bsdf(int device, uint32_t n, const float *mat10, const float *N, const float *wo, const float *wi,
+                      const uint32_t *state, const float *dist, float roughness,
+                      float *sample_wi, int32_t *is_transmission, uint32_t *state_after, float *pdf, float *eval);
 
 /* ------------------------------------------------------------------------
  * Scene hand-off.
@@ -140,6 +172,7 @@ int ort_scene_build_stats(const OrtScene *scene, OrtBuildStats *out);
 int ort_scene_download(OrtScene *scene, void *nodes, uint64_t nodes_bytes, void *prims, uint64_t prims_bytes);
 int ort_scene_destroy(OrtScene *scene);
 int ort_scene_info(const OrtScene *scene, OrtSceneInfo *info);
+int ort_scene_device(const OrtScene *scene, int *device);
 
 /* ------------------------------------------------------------------------
  * Render entry point, reference signature.
@@ -153,9 +186,10 @@ int ort_scene_info(const OrtScene *scene, OrtSceneInfo *info);
  * output_width*output_height pixels, row 0 = bottom of the picture; only the
  * tile's pixels are written, each with the mean radiance over
  * ray_per_pixel_count samples.  *test_shape_count receives the number of
- * primitive tests executed (the reference's return value has the same meaning
- * for its own octree; the counts differ because the acceleration structure
- * differs).
+ * primitive (shape) tests executed -- the reference's return value, summed as at
+ * ray.cpp:661-715, 1173; the tally is far smaller than the reference's for the
+ * same image because the rebuilt acceleration structure culls better.  It may be
+ * called from several host threads at once on disjoint tiles (see THREADS above).
  *
  * RNG: the reference shares one sequential RandomSeries between all pixels of
  * the tile, which cannot be parallelised.  Here the series' current state is
@@ -232,9 +266,8 @@ int ort_render(OrtScene *scene, const OrtCamera *camera, const OrtRenderParams *
  * fixed-point buffer on the scene's device (zero it first with
  * ort_accum_zero_device).  The work is ordered after whatever the caller queued on
  * CUDA stream `stream` (a cudaStream_t passed as void*, NULL = default stream); the
- * call returns when the chunk range is done (the wavefront loop reads its "paths
- * still alive" counter on the host), so the caller's next launch on any stream
- * sees the sums.  After the sum over ranks (ncclSum on int64 is
+ * call returns when the chunk range is done, whichever kernel family ran it (it
+ * synchronises `stream`), so the caller's next launch on any stream sees the sums.  After the sum over ranks (ncclSum on int64 is
  * exact), ort_accum_resolve_device writes float3 pixels = sum / spp. */
 int ort_render_accumulate_device(OrtScene *scene, const OrtCamera *camera,
                                  const OrtRenderParams *params, void *accum_device,
@@ -273,6 +306,78 @@ int ort_raycast_brute_device(OrtScene *scene, uint64_t n, const float *origins, 
  * primitive tests. */
 int ort_raycast_counters_device(OrtScene *scene, uint64_t n, const float *origins, const float *dirs,
                                 uint64_t *node_visits, uint64_t *box_tests, uint64_t *shape_tests);
+
+/* Explicit ray buffers of the traversal microbenchmark (BASELINE config 2), generated on `device`
+ * into device arrays of n xyz triples; ray i draws from its own xorshift stream
+ * ort_stream_seed(seed, i, 0) (code/random.h:5-38).
+ *   camera rays: ray i is a sample of pixel (i % w, i / w) of the params' w x h grid from the
+ *     reference camera model with its depth-of-field lens sample (code/ray.cpp:1215-1246) -- the
+ *     render kernels' own generate code; n <= w*h.
+ *   random rays: origin uniform in [box_min, box_max], direction uniform on the sphere. */
+int ort_generate_camera_rays_device(int device, const OrtCamera *camera, const OrtRenderParams *params, uint32_t seed,
+                                    uint64_t n, float *origins_device, float *dirs_device, void *stream);
+int ort_generate_random_rays_device(int device, const float box_min[3], const float box_max[3], uint32_t seed,
+                                    uint64_t n, float *origins_device, float *dirs_device, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU.  The path shards with no data-path dependency: the
+ * scene is replicated, GPU r renders its own range of sample chunks of the same
+ * frame into its own int64 fixed-point framebuffer, and the framebuffers are
+ * summed.  The sum is ONE kernel on the root GPU that reads the peers'
+ * framebuffers in place over NVLink peer memory, adds them into the root's and
+ * resolves in the same pass (float3 pixels and/or RGBE words) -- integer addition,
+ * hence bit-identical to the 1-GPU image for any number of GPUs.
+ * Replaces the reference's nine tile workers on one shared-memory machine
+ * (code/macos_main.mm:165-240, 574-671).
+ *
+ * (a) one process per GPU: every process allocates its framebuffer with
+ *     ort_accum_alloc_device, exports a CUDA IPC handle (ort_accum_ipc_export), the
+ *     host-side plumbing moves the 64-byte handles to the root, which opens them once
+ *     (ort_accum_ipc_open) and calls ort_accum_reduce_resolve_device after the ranks
+ *     have finished their ort_render_accumulate_device (a barrier of the plumbing).
+ * (b) one process, N devices: OrtMulti below.
+ * ---------------------------------------------------------------------- */
+#define ORT_IPC_HANDLE_BYTES 64
+int ort_accum_alloc_device(OrtScene *scene, int32_t width, int32_t height, void **accum_device);   /* zeroed */
+int ort_accum_free_device(OrtScene *scene, void *accum_device);
+int ort_accum_ipc_export(OrtScene *scene, const void *accum_device, uint8_t handle[ORT_IPC_HANDLE_BYTES]);
+int ort_accum_ipc_open(OrtScene *scene, const uint8_t handle[ORT_IPC_HANDLE_BYTES], void **peer_accum);
+int ort_accum_ipc_close(OrtScene *scene, void *peer_accum);
+/* accum_device += sum of the n_peers peer framebuffers (device pointers readable from the scene's
+ * device: peer access or opened IPC handles); rgb_device / rgbe_device, when not NULL, receive the
+ * resolved image (sum / spp as float3, row 0 = bottom; RGBE words in .hdr file order).  Asynchronous
+ * on `stream`.  n_peers = 0 is a plain resolve. */
+int ort_accum_reduce_resolve_device(OrtScene *scene, void *accum_device, const void *const *peer_accums, uint32_t n_peers,
+                                    int32_t width, int32_t height, uint32_t ray_per_pixel_count,
+                                    void *rgb_device, void *rgbe_device, void *stream);
+
+/* (b) N devices in one process.  scenes[i] are handles of the SAME scene on distinct devices; scenes[0]'s
+ * device is the root.  ort_multi_render = ort_render for a whole image with the sample chunks split over
+ * the devices (set params->chunk_spp; with a single chunk only one device has work).  The image is
+ * bit-identical to ort_render's on one GPU with the same params whenever the frame has more than one chunk. */
+typedef struct OrtMulti OrtMulti;
+int ort_multi_create(OrtScene *const *scenes, uint32_t n, OrtMulti **out);
+int ort_multi_destroy(OrtMulti *multi);
+int ort_multi_device_count(const OrtMulti *multi, uint32_t *n_devices, uint32_t *n_peer_direct);
+int ort_multi_render(OrtMulti *multi, const OrtCamera *camera, const OrtRenderParams *params,
+                     ort_v3 *output_buffer, OrtRenderStats *stats);
+
+/* Progressive accumulation with dynamic chunk dispatch and checkpoint / resume (the
+ * reference's ThreadWorkQueue, code/platform.h:307-339, hands out 32x32 tiles and cannot stop and
+ * continue).  The unit of work is a chunk index: ort_progress_render lets every device of the OrtMulti
+ * pull the next unrendered chunk from a shared counter until max_chunks more are done (0 = all that
+ * remain); ort_progress_resolve returns the image of the chunks done so far (sum / samples done);
+ * ort_progress_save / ort_progress_load write / read a checkpoint (format: csrc/ort_multi.cu) from which
+ * any number of devices continues.  Chunks may be rendered in any order, by any device, in any number of
+ * sessions: the final image is bit-identical to ort_render's.  One OrtProgress at a time per OrtMulti. */
+typedef struct OrtProgress OrtProgress;
+int ort_progress_create(OrtMulti *multi, const OrtCamera *camera, const OrtRenderParams *params, OrtProgress **out);
+int ort_progress_destroy(OrtProgress *progress);
+int ort_progress_render(OrtProgress *progress, uint32_t max_chunks, OrtRenderStats *stats);
+int ort_progress_state(const OrtProgress *progress, uint32_t *chunks_done, uint32_t *chunks_total, uint32_t *spp_done);
+int ort_progress_resolve(OrtProgress *progress, ort_v3 *output_buffer);
+int ort_progress_save(OrtProgress *progress, const char *path);
+int ort_progress_load(OrtMulti *multi, const char *path, OrtProgress **out);
 
 /* ------------------------------------------------------------------------
  * Host side of the drop-in: this library's own re-implementation of the

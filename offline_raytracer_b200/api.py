@@ -137,6 +137,29 @@ def lib(path=None):
     L.ort_raycast_batch_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp, vp]
     L.ort_raycast_brute_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp]
     L.ort_raycast_counters_device.argtypes = [vp, c_u64, vp, vp, C.POINTER(c_u64), C.POINTER(c_u64), C.POINTER(c_u64)]
+    L.ort_scene_device.argtypes = [vp, C.POINTER(C.c_int)]
+    L.ort_measure_l2_bandwidth.argtypes = [C.c_int, c_u32, C.POINTER(c_f)]
+    L.ort_selftest_intersect.argtypes = [C.c_int, c_u32, c_u32, vp, vp]
+    L.ort_selftest_bsdf.argtypes = [C.c_int, c_u32, vp, vp, vp, vp, vp, vp, c_f, vp, vp, vp, vp, vp]
+    L.ort_generate_camera_rays_device.argtypes = [C.c_int, vp, C.POINTER(RenderParams), c_u32, c_u64, vp, vp, vp]
+    L.ort_generate_random_rays_device.argtypes = [C.c_int, C.POINTER(c_f), C.POINTER(c_f), c_u32, c_u64, vp, vp, vp]
+    L.ort_accum_alloc_device.argtypes = [vp, c_i32, c_i32, C.POINTER(vp)]
+    L.ort_accum_free_device.argtypes = [vp, vp]
+    L.ort_accum_ipc_export.argtypes = [vp, vp, vp]
+    L.ort_accum_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.ort_accum_ipc_close.argtypes = [vp, vp]
+    L.ort_accum_reduce_resolve_device.argtypes = [vp, vp, C.POINTER(vp), c_u32, c_i32, c_i32, c_u32, vp, vp, vp]
+    L.ort_multi_create.argtypes = [C.POINTER(vp), c_u32, C.POINTER(vp)]
+    L.ort_multi_destroy.argtypes = [vp]
+    L.ort_multi_device_count.argtypes = [vp, C.POINTER(c_u32), C.POINTER(c_u32)]
+    L.ort_multi_render.argtypes = [vp, vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
+    L.ort_progress_create.argtypes = [vp, vp, C.POINTER(RenderParams), C.POINTER(vp)]
+    L.ort_progress_destroy.argtypes = [vp]
+    L.ort_progress_render.argtypes = [vp, c_u32, C.POINTER(RenderStats)]
+    L.ort_progress_state.argtypes = [vp, C.POINTER(c_u32), C.POINTER(c_u32), C.POINTER(c_u32)]
+    L.ort_progress_resolve.argtypes = [vp, vp]
+    L.ort_progress_save.argtypes = [vp, C.c_char_p]
+    L.ort_progress_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     if hasattr(L, "ort_host_scene_load"):
         L.ort_host_scene_load.argtypes = [C.c_char_p, C.c_char_p, c_i32, c_i32, C.c_int, C.POINTER(vp)]
         L.ort_host_scene_destroy.argtypes = [vp]
@@ -176,6 +199,52 @@ def measure_fp32_peak(device=0):
     v = c_f(0)
     _check(L.ort_measure_fp32_peak(device, C.byref(v), None))
     return float(v.value)
+
+
+def measure_l2_bandwidth(device=0, buffer_mib=32):
+    """GB/s of the L2-resident streaming-read microbenchmark: the L2 roofline denominator"""
+    v = c_f(0)
+    _check(lib().ort_measure_l2_bandwidth(device, buffer_mib, C.byref(v)))
+    return float(v.value)
+
+
+_ISECT_KIND = {"triangle": (0, 15), "sphere": (1, 10), "aab": (2, 12), "cylinder": (3, 13)}
+
+
+def selftest_intersect(kind, cases, device=0):
+    """the DEVICE build of the intersector `kind` on explicit cases [n, stride] -> [n, 5] = t, normal xyz, inner"""
+    k, stride = _ISECT_KIND[kind]
+    a = np.ascontiguousarray(cases, np.float32).reshape(-1, stride)
+    out = np.zeros((a.shape[0], 5), np.float32)
+    _check(lib().ort_selftest_intersect(device, k, a.shape[0], _ptr(a), _ptr(out)))
+    return out
+
+
+def selftest_bsdf(mat10, N, wo, wi, state, dist, roughness=0.01, device=0):
+    """the DEVICE build of sample_brdf / pdf_brdf / eval_scattering (csrc/path.h) on explicit tuples"""
+    f = lambda x, w: np.ascontiguousarray(x, np.float32).reshape(-1, w)
+    m, N, wo, wi = f(mat10, 10), f(N, 3), f(wo, 3), f(wi, 3)
+    n = m.shape[0]
+    st = np.ascontiguousarray(state, np.uint32).reshape(n)
+    d = np.ascontiguousarray(dist, np.float32).reshape(n)
+    s_wi = np.zeros((n, 3), np.float32); is_t = np.zeros(n, np.int32); st2 = np.zeros(n, np.uint32)
+    pdf = np.zeros(n, np.float32); ev = np.zeros((n, 3), np.float32)
+    _check(lib().ort_selftest_bsdf(device, n, _ptr(m), _ptr(N), _ptr(wo), _ptr(wi), _ptr(st), _ptr(d), c_f(roughness),
+                                   _ptr(s_wi), _ptr(is_t), _ptr(st2), _ptr(pdf), _ptr(ev)))
+    return dict(sample_wi=s_wi, is_transmission=is_t, state_after=st2, pdf=pdf, eval=ev)
+
+
+def generate_camera_rays_device(camera_ptr, params, seed, n, origins_ptr, dirs_ptr, device=0, stream=None):
+    """BASELINE config 2, coherent buffer: n lens-sampled primaries of the params' w x h grid (device arrays)"""
+    _check(lib().ort_generate_camera_rays_device(device, _as_ptr(camera_ptr), C.byref(params), seed, n,
+                                                 vp(origins_ptr), vp(dirs_ptr), vp(stream) if stream else None))
+
+
+def generate_random_rays_device(box_min, box_max, seed, n, origins_ptr, dirs_ptr, device=0, stream=None):
+    """BASELINE config 2, incoherent buffer: origins uniform in the box, directions uniform on the sphere"""
+    lo = (c_f * 3)(*[float(x) for x in box_min]); hi = (c_f * 3)(*[float(x) for x in box_max])
+    _check(lib().ort_generate_random_rays_device(device, lo, hi, seed, n, vp(origins_ptr), vp(dirs_ptr),
+                                                 vp(stream) if stream else None))
 
 
 def selftest_div3(triples=1 << 28, seed=12345, device=0):
@@ -371,6 +440,38 @@ class Scene:
         _check(self.L.ort_accum_resolve_device(self.h, vp(accum_ptr), width, height, spp, vp(rgb_ptr),
                                                vp(stream) if stream else None), self.L)
 
+    # -- multi-GPU: framebuffers shared over NVLink peer memory ---------------------
+    def accum_alloc_device(self, width, height):
+        p = vp(0)
+        _check(self.L.ort_accum_alloc_device(self.h, width, height, C.byref(p)), self.L)
+        return p.value
+
+    def accum_free_device(self, accum_ptr):
+        _check(self.L.ort_accum_free_device(self.h, vp(accum_ptr)), self.L)
+
+    def accum_ipc_export(self, accum_ptr):
+        """64-byte CUDA IPC handle of a framebuffer from accum_alloc_device (bytes)"""
+        h = (C.c_uint8 * 64)()
+        _check(self.L.ort_accum_ipc_export(self.h, vp(accum_ptr), h), self.L)
+        return bytes(h)
+
+    def accum_ipc_open(self, handle_bytes):
+        h = (C.c_uint8 * 64)(*handle_bytes)
+        p = vp(0)
+        _check(self.L.ort_accum_ipc_open(self.h, h, C.byref(p)), self.L)
+        return p.value
+
+    def accum_ipc_close(self, peer_ptr):
+        _check(self.L.ort_accum_ipc_close(self.h, vp(peer_ptr)), self.L)
+
+    def accum_reduce_resolve_device(self, accum_ptr, peer_ptrs, width, height, spp, rgb_ptr=0, rgbe_ptr=0, stream=None):
+        """accum += sum(peers) and resolve, one kernel reading the peers' framebuffers in place"""
+        n = len(peer_ptrs)
+        arr = (vp * max(n, 1))(*[vp(p) for p in peer_ptrs])
+        _check(self.L.ort_accum_reduce_resolve_device(self.h, vp(accum_ptr), arr, n, width, height, spp,
+                                                      vp(rgb_ptr) if rgb_ptr else None, vp(rgbe_ptr) if rgbe_ptr else None,
+                                                      vp(stream) if stream else None), self.L)
+
     # -- ray cast ---------------------------------------------------------------
     def raycast_batch(self, origins, dirs, want_normal=True):
         """ort_raycast_batch on host arrays [n,3]; returns dict(t, rank, mat, normal, device_ms)"""
@@ -400,6 +501,78 @@ class Scene:
         _check(self.L.ort_raycast_counters_device(self.h, n, vp(origins_ptr), vp(dirs_ptr),
                                                   C.byref(a), C.byref(b), C.byref(c)), self.L)
         return dict(node_visits=a.value, box_tests=b.value, shape_tests=c.value)
+
+
+class Multi:
+    """OrtMulti: the same scene on several devices of this process (ort_multi_*)"""
+
+    def __init__(self, scenes):
+        self.L = scenes[0].L
+        self.scenes = list(scenes)
+        arr = (vp * len(scenes))(*[sc.h for sc in scenes])
+        h = vp(0)
+        _check(self.L.ort_multi_create(arr, len(scenes), C.byref(h)), self.L)
+        self.h = h
+
+    def device_count(self):
+        n, d = c_u32(0), c_u32(0)
+        _check(self.L.ort_multi_device_count(self.h, C.byref(n), C.byref(d)), self.L)
+        return n.value, d.value
+
+    def render(self, camera_ptr, params, out=None):
+        W, H = params.output_width, params.output_height
+        if out is None:
+            out = np.zeros((H, W, 3), np.float32)
+        st = RenderStats()
+        _check(self.L.ort_multi_render(self.h, _as_ptr(camera_ptr), C.byref(params), _ptr(out), C.byref(st)), self.L)
+        return out, st.as_dict()
+
+    def close(self):
+        if self.h:
+            self.L.ort_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Progress:
+    """OrtProgress: progressive accumulation, dynamic chunk dispatch, checkpoint / resume (ort_progress_*)"""
+
+    def __init__(self, multi, camera_ptr=None, params=None, path=None):
+        self.L, self.multi = multi.L, multi
+        h = vp(0)
+        if path is not None:
+            _check(self.L.ort_progress_load(multi.h, str(path).encode(), C.byref(h)), self.L)
+        else:
+            _check(self.L.ort_progress_create(multi.h, _as_ptr(camera_ptr), C.byref(params), C.byref(h)), self.L)
+        self.h = h
+
+    def render(self, max_chunks=0):
+        st = RenderStats()
+        _check(self.L.ort_progress_render(self.h, max_chunks, C.byref(st)), self.L)
+        return st.as_dict()
+
+    def state(self):
+        a, b, c = c_u32(0), c_u32(0), c_u32(0)
+        _check(self.L.ort_progress_state(self.h, C.byref(a), C.byref(b), C.byref(c)), self.L)
+        return dict(chunks_done=a.value, chunks_total=b.value, spp_done=c.value)
+
+    def resolve(self, width, height):
+        out = np.zeros((height, width, 3), np.float32)
+        _check(self.L.ort_progress_resolve(self.h, _ptr(out)), self.L)
+        return out
+
+    def save(self, path):
+        _check(self.L.ort_progress_save(self.h, str(path).encode()), self.L)
+
+    def close(self):
+        if self.h:
+            self.L.ort_progress_destroy(self.h)
+            self.h = None
 
 
 def load_mesh(path):

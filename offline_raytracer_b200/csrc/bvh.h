@@ -202,7 +202,9 @@ ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
 // the node group and returns the hit leaf primitives as a group (base index, bit mask) plus the
 // index of the node visited (its tree decides the kind of the primitives and whether clip_t
 // applies: nodes below main_root -- the sphere tree -- are never clipped).
-template <bool COUNT, class Stack>
+// COUNT: 0 = no counters, 1 = all three (the counters build), 2 = primitive tests only (the product
+// build: the reference's entry point returns that tally, ray.cpp:661-715, 1173)
+template <int COUNT, class Stack>
 ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, TraceCounters *cnt,
                        uint32_t *tg_x_out, uint32_t *tg_y_out, uint32_t *node_index_out, uint32_t *mixed_out = 0)
 {
@@ -228,7 +230,7 @@ ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, Tra
     const float t_clip = (node_index >= s.main_root) ? clip_t : FLT_MAX;
     const q4 *np = s.nodes + 5u * node_index;
     q4 n0 = ldq(np), n1 = ldq(np + 1), n2 = ldq(np + 2), n3 = ldq(np + 3), n4 = ldq(np + 4);
-    if(COUNT) cnt->node_visits++;
+    if(COUNT == 1) cnt->node_visits++;
 
     uint32_t e_imask = f2u(n0.w);
     float ax = u2f((e_imask & 0xFFu) << 23) * idx;
@@ -271,7 +273,7 @@ ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, Tra
             float t1z = fmaf(ORT_I2F_PLANES >= 1 ? byte_f_xu(farz, k) : byte_f(farz, k), az, bz);
             float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
             float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
-            if(COUNT) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
+            if(COUNT == 1) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
             uint32_t child_bits = (child_bits4 >> (8u * k)) & 0xFFu;
             uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
             hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
@@ -297,7 +299,7 @@ ORT_HD bool trav_next(Trav &t, Stack &st)
 
 // One step: visit one wide node, test the primitives it yielded, pop.  Returns true when the
 // traversal is complete.
-template <bool COUNT, class Stack>
+template <int COUNT, class Stack>
 ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt)
 {
     uint32_t tg_x = 0u, tg_y = 0u, node_index = 0u;
@@ -309,7 +311,7 @@ ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt
         uint32_t prim = tg_x + bit, rank, mat;
         exact::Hit h = intersect_prim(s, prim, t.o, t.d, t.inv, &rank, &mat);
         (void)mat;
-        if(COUNT) cnt->shape_tests++;
+        if(COUNT != 0) cnt->shape_tests++;
         // ray.cpp:653,670,686,708: t >= 1e-6 && t < best; exact ties -> lowest rank
         if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < t.best_t || (h.t == t.best_t && rank < t.best_rank)))
         {
@@ -321,7 +323,7 @@ ORT_HD bool trav_step(const SceneView &s, Trav &t, Stack &st, TraceCounters *cnt
 
 // Closest hit.  COUNT adds work counters (the counters build of the same code,
 // SURVEY.md 8d).  o/d as in raycast_top_most_node; d need not be unit.
-template <bool COUNT>
+template <int COUNT>
 ORT_HD void trace(const SceneView &s, f3 o, f3 d, TraceHit *hit, TraceCounters *cnt)
 {
     Trav t; LocalStack st;

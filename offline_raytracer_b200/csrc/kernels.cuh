@@ -41,7 +41,7 @@ k_raycast(SceneView scene, unsigned long long n, const float *__restrict__ origi
         f3 o = mk3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         f3 d = mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         TraceHit hit; TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
-        trace<COUNT>(scene, o, d, &hit, &cnt);
+        trace<COUNT ? 1 : 0>(scene, o, d, &hit, &cnt);
         if(hit_t) hit_t[i] = hit.t;
         if(prim_rank) prim_rank[i] = hit.rank;
         if(mat_index || hit_normal)
@@ -214,9 +214,10 @@ k_render_mega(const RenderArgs a)
         }
         // ---- extend (ray.cpp:1249, 1352) ----
         TraceHit hit; TraceCounters cnt; cnt.node_visits = cnt.box_tests = cnt.shape_tests = 0;
-        trace<COUNT>(a.scene, p.origin, p.dir, &hit, &cnt);
+        trace<COUNT ? 1 : 2>(a.scene, p.origin, p.dir, &hit, &cnt);
         ++n_rays;
-        if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; shapes += cnt.shape_tests; }
+        shapes += cnt.shape_tests;           // always: the reference's entry point returns this tally (ray.cpp:1173)
+        if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; }
         uint32_t mat; f3 nrm;
         finish_hit(a.scene, hit, p.origin, p.dir, &mat, &nrm);
         // ---- shade (ray.cpp:1251-1277, 1355-1421) + head of the next bounce (ray.cpp:1280-1349) ----
@@ -226,17 +227,17 @@ k_render_mega(const RenderArgs a)
         have_ray = alive && next_bounce(a.pc, &p);
     }
 
-    n_rays = warp_sum(n_rays); n_samples = warp_sum(n_samples);
-    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); shapes = warp_sum(shapes); }
+    n_rays = warp_sum(n_rays); n_samples = warp_sum(n_samples); shapes = warp_sum(shapes);
+    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); }
     if((threadIdx.x & 31) == 0)
     {
         atomicAdd(&a.stats[STAT_RAYS], n_rays);
         atomicAdd(&a.stats[STAT_SAMPLES], n_samples);
+        atomicAdd(&a.stats[STAT_SHAPE_TESTS], shapes);
         if(COUNT)
         {
             atomicAdd(&a.stats[STAT_NODE_VISITS], nodes);
             atomicAdd(&a.stats[STAT_BOX_TESTS], boxes);
-            atomicAdd(&a.stats[STAT_SHAPE_TESTS], shapes);
         }
     }
 }

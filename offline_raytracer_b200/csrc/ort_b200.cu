@@ -9,7 +9,9 @@
 #include <vector>
 #include <chrono>
 #include <algorithm>
+#include <mutex>
 
+#include "ort_internal.h"
 #include "wavefront.cuh"
 #include "bvh_build.cuh"
 #include "scene_flatten.h"
@@ -83,6 +85,11 @@ struct OrtScene
     WfPool pools[WF_MAX_POOLS];
     int wf_ready;
     cudaEvent_t wf_start;
+    // The handle's scratch (framebuffers, counters, slot pools, streams, events) is shared by all
+    // entry points, so every entry point that touches it holds this lock for the whole call: the
+    // handle may be used from any number of host threads -- e.g. the reference's nine tile workers
+    // (code/macos_main.mm:574-598) -- and their calls are serialised (the GPU would serialise them anyway).
+    std::recursive_mutex *mu;
 
     SceneView view() const
     {
@@ -94,6 +101,12 @@ struct OrtScene
 };
 
 namespace {
+
+struct SceneLock
+{
+    std::lock_guard<std::recursive_mutex> guard;
+    explicit SceneLock(OrtScene *s) : guard(*s->mu) {}
+};
 
 template <typename T>
 int upload(T **dst, const void *src, size_t bytes, uint64_t *total)
@@ -576,6 +589,7 @@ static int make_scene_handle(FlatScene &flat, build::DeviceBuildResult &built, b
     int rc = ORT_OK;
     OrtScene *s = new OrtScene();
     memset(s, 0, sizeof(*s));
+    s->mu = new std::recursive_mutex();
     s->device = device;
     s->info = flat.info;
     s->build_stats = bs;
@@ -750,7 +764,15 @@ int ort_scene_destroy(OrtScene *s)
     if(s->ev0) cudaEventDestroy(s->ev0);
     if(s->ev1) cudaEventDestroy(s->ev1);
     if(s->stream) cudaStreamDestroy(s->stream);
+    delete s->mu;
     delete s;
+    return ORT_OK;
+}
+
+int ort_scene_device(const OrtScene *s, int *device)
+{
+    if(!s || !device) return fail(ORT_ERR_ARG, "null argument");
+    *device = s->device;
     return ORT_OK;
 }
 
@@ -817,6 +839,7 @@ int ort_render(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *P, o
     if(!s || !camera || !output_buffer) return fail(ORT_ERR_ARG, "null argument");
     int rc = check_params(P);
     if(rc != ORT_OK) return rc;
+    SceneLock lock(s);
     CUDA_TRY(cudaSetDevice(s->device));
     int tw = P->tile_one_past_max_x - P->tile_min_x, th = P->tile_one_past_max_y - P->tile_min_y;
     uint32_t launches = 0;
@@ -870,6 +893,7 @@ int ort_render_rgbe(OrtScene *s, const OrtCamera *camera, const OrtRenderParams 
     if(rc != ORT_OK) return rc;
     if(P->tile_min_x != 0 || P->tile_min_y != 0 || P->tile_one_past_max_x != P->output_width || P->tile_one_past_max_y != P->output_height)
         return fail(ORT_ERR_ARG, "ort_render_rgbe renders whole images: the tile must cover the output");
+    SceneLock lock(s);
     CUDA_TRY(cudaSetDevice(s->device));
     size_t pixels = (size_t)P->output_width * P->output_height;
     if(s->rgbe_capacity < pixels)
@@ -915,6 +939,8 @@ int ort_tiled_raytrace_bvh(OrtScene *scene, const OrtCamera *camera, ort_v3 *out
                            uint64_t *test_shape_count)
 {
     if(!series) return fail(ORT_ERR_ARG, "series is null");
+    if(!scene) return fail(ORT_ERR_ARG, "null scene");
+    SceneLock lock(scene);
     OrtRenderParams P;
     ort_render_params_default(&P, output_width, output_height, ray_per_pixel_count);
     P.tile_min_x = tile_min_x; P.tile_min_y = tile_min_y;
@@ -925,7 +951,7 @@ int ort_tiled_raytrace_bvh(OrtScene *scene, const OrtCamera *camera, ort_v3 *out
     int rc = ort_render(scene, camera, &P, output_buffer, &st);
     if(rc != ORT_OK) return rc;
     xor_shift_32(&series->next_random);
-    if(test_shape_count) *test_shape_count = st.shape_tests ? st.shape_tests : st.rays;
+    if(test_shape_count) *test_shape_count = st.shape_tests;     // primitive tests executed, as ray.cpp:661-715, 1173
     return ORT_OK;
 }
 
@@ -943,6 +969,7 @@ int ort_render_accumulate_device(OrtScene *s, const OrtCamera *camera, const Ort
     if(!s || !camera || !accum_device) return fail(ORT_ERR_ARG, "null argument");
     int rc = check_params(P);
     if(rc != ORT_OK) return rc;
+    SceneLock lock(s);
     CUDA_TRY(cudaSetDevice(s->device));
     ChunkPlan cp = plan_chunks(P);
     cudaStream_t st = (cudaStream_t)stream;
@@ -952,9 +979,13 @@ int ort_render_accumulate_device(OrtScene *s, const OrtCamera *camera, const Ort
     rc = launch_render(s, camera, P, cp, (long long *)accum_device, 0, st, &launches);
     if(rc != ORT_OK) return rc;
     CUDA_TRY(cudaEventRecord(s->ev1, st));
+    // The call returns when the chunk range is done, whichever kernel family ran it (the wavefront loop
+    // has host-synchronised its pools already; the single-launch megakernel is waited for here): the
+    // sums are visible to the caller's next launch on any stream, and the handle's counters are free
+    // for the next call.
+    CUDA_TRY(cudaStreamSynchronize(st));
     if(stats)
     {
-        CUDA_TRY(cudaStreamSynchronize(st));
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         return read_stats(s, st, stats, ms, launches);
@@ -1006,6 +1037,7 @@ int ort_raycast_counters_device(OrtScene *s, uint64_t n, const float *origins, c
                                 uint64_t *node_visits, uint64_t *box_tests, uint64_t *shape_tests)
 {
     if(!s || (n && (!origins || !dirs))) return fail(ORT_ERR_ARG, "null argument");
+    SceneLock lock(s);
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
     CUDA_TRY(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
@@ -1030,6 +1062,7 @@ int ort_raycast_batch(OrtScene *s, uint64_t n, const float *origins, const float
                       float *hit_t, uint32_t *prim_rank, uint32_t *mat_index, float *hit_normal, OrtRenderStats *stats)
 {
     if(!s || (n && (!origins || !dirs))) return fail(ORT_ERR_ARG, "null argument");
+    SceneLock lock(s);
     CUDA_TRY(cudaSetDevice(s->device));
     if(stats) memset(stats, 0, sizeof(*stats));
     if(n == 0) return ORT_OK;

@@ -109,6 +109,8 @@ static void material_constants(DevMaterial *dm)
     dm->lobes = (length_square(Kd) > 0.0f ? 1u : 0u) | (length_square(Ks) > 0.0f ? 2u : 0u) | (length_square(Kt) > 0.0f ? 4u : 0u);
 }
 
+void material_constants_public(DevMaterial *dm) { material_constants(dm); }   // ort_tools.cu (device BSDF harness)
+
 // world-level tables of the flattened scene: materials and the light list
 static int fill_world_tables(const OrtWorld *world, FlatScene *out, std::string *err)
 {

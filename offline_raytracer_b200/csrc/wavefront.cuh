@@ -144,7 +144,8 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
 #if ORT_EXTEND_ONE_PRIM
     uint32_t pg_x = 0u, pg_y = 0u;
 #endif
-    unsigned long long nodes = 0, boxes = 0, shapes = 0, rays = 0;
+    unsigned long long nodes = 0, boxes = 0;
+    uint32_t shapes = 0, rays = 0;          // per thread and launch: far below 2^32
 
     for(;;)
     {
@@ -198,7 +199,7 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
                 if(pg_y == 0u && (t.ng_y & 0xFF000000u))
                 {
                     uint32_t node_index;
-                    trav_visit<COUNT>(scene, t, st, t.best_t, &cnt, &pg_x, &pg_y, &node_index);
+                    trav_visit<COUNT ? 1 : 0>(scene, t, st, t.best_t, &cnt, &pg_x, &pg_y, &node_index);
                 }
                 if(pg_y != 0u)
                 {
@@ -206,7 +207,7 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
                     pg_y &= pg_y - 1u;
                     exact::Hit h = intersect_prim(scene, prim, t.o, t.d, t.inv, &rank, &mat);
                     (void)mat;
-                    if(COUNT) cnt.shape_tests++;
+                    ++shapes;                // always: ort_tiled_raytrace_bvh returns this tally (ray.cpp:1173)
                     if(h.t >= ORT_HIT_T_THRESHOLD && (h.t < t.best_t || (h.t == t.best_t && rank < t.best_rank)))
                     {
                         t.best_t = h.t; t.best_prim = prim; t.best_rank = rank;
@@ -215,9 +216,10 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
                 if(pg_y == 0u) done = !trav_next(t, st);
             }
 #else
-            bool done = has_ray && trav_step<COUNT>(scene, t, st, &cnt);
+            bool done = has_ray && trav_step<COUNT ? 1 : 2>(scene, t, st, &cnt);
+            shapes += cnt.shape_tests;
 #endif
-            if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; shapes += cnt.shape_tests; }
+            if(COUNT) { nodes += cnt.node_visits; boxes += cnt.box_tests; }
             if(done)
             {
                 uint32_t mat = 0u;
@@ -230,16 +232,17 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
             }
         }
     }
-    rays = warp_sum(rays);
-    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); shapes = warp_sum(shapes); }
+    rays = __reduce_add_sync(0xFFFFFFFFu, rays);
+    shapes = __reduce_add_sync(0xFFFFFFFFu, shapes);
+    if(COUNT) { nodes = warp_sum(nodes); boxes = warp_sum(boxes); }
     if(lane == 0 && rays)
     {
-        atomicAdd(&stats[STAT_RAYS], rays);
+        atomicAdd(&stats[STAT_RAYS], (unsigned long long)rays);
+        atomicAdd(&stats[STAT_SHAPE_TESTS], (unsigned long long)shapes);
         if(COUNT)
         {
             atomicAdd(&stats[STAT_NODE_VISITS], nodes);
             atomicAdd(&stats[STAT_BOX_TESTS], boxes);
-            atomicAdd(&stats[STAT_SHAPE_TESTS], shapes);
         }
     }
     // the block's share of the key histogram (first pass of the counting sort), flushed by

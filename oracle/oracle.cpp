@@ -1060,4 +1060,45 @@ uint32_t oracle_sample_random_lights(void *h, uint32_t state)
 }
 int64_t oracle_to_fixed(float v) { return to_fixed(v); }
 
+// Explicit ray buffers of BASELINE config 2, generated ONCE here and shared by every side:
+//  kind 0, coherent: ray i = a lens-sampled primary of pixel (i % w, i / w) of the params' w x h grid, the
+//          camera model of ray.cpp:1215-1237, lens angle from the reference xorshift (random.h) seeded per ray
+//          with ort_stream_seed(seed, i, 0);
+//  kind 1, incoherent: origin uniform in [lo, hi], direction uniform on the sphere, same per-ray streams.
+void oracle_make_rays(int kind, const OrtCamera *cam, const OrtRenderParams *P, const float *lo, const float *hi,
+                      uint32_t seed, uint64_t n, float *origins, float *dirs)
+{
+    for(uint64_t i = 0; i < n; ++i)
+    {
+        u32 s = ort_stream_seed(seed, (uint32_t)i, (uint32_t)(i >> 32));
+        V3 o, d;
+        if(kind == 0)
+        {
+            int x = (int)(i % (uint64_t)P->output_width), y = (int)(i / (uint64_t)P->output_width);
+            f32 focal_length = len(sub(cam->p, mk(P->focus_target[0], P->focus_target[1], P->focus_target[2])));
+            f32 pixel_x = (2.0f * x / (f32)P->output_width) - 1.0f;
+            f32 pixel_y = (2.0f * y / (f32)P->output_height) - 1.0f;
+            V3 camera_to_pixel = normalize(sub(add(mul(pixel_x, cam->x_axis), mul(pixel_y, cam->y_axis)), cam->z_axis));
+            V3 focal_point = add(cam->p, mul(focal_length, camera_to_pixel));
+            f32 random_rad = rnd_between(&s, 0.0f, 2 * PI_32);
+            o = sub(add(add(cam->p, mul(P->aperture_radius * cosf(random_rad), cam->x_axis)),
+                        mul(P->aperture_radius * sinf(random_rad), cam->y_axis)), mul(P->lens_z_offset, cam->z_axis));
+            d = normalize(sub(focal_point, o));
+        }
+        else
+        {
+            o.x = lo[0] + (hi[0] - lo[0]) * rnd01(&s);
+            o.y = lo[1] + (hi[1] - lo[1]) * rnd01(&s);
+            o.z = lo[2] + (hi[2] - lo[2]) * rnd01(&s);
+            f32 z = 2.0f * rnd01(&s) - 1.0f;
+            f32 phi = 2.0f * PI_32 * rnd01(&s);
+            f32 r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+            d = normalize(mk(r * cosf(phi), r * sinf(phi), z));
+            if(d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) d = mk(0, 0, 1);
+        }
+        origins[3 * i] = o.x; origins[3 * i + 1] = o.y; origins[3 * i + 2] = o.z;
+        dirs[3 * i] = d.x; dirs[3 * i + 1] = d.y; dirs[3 * i + 2] = d.z;
+    }
+}
+
 } // extern "C"

@@ -303,10 +303,24 @@ class Oracle(_FuncsMixin):
         lib.oracle_accum_resolve.argtypes = [vp, C.c_int, C.c_int, c_u32, vp]
         lib.oracle_to_fixed.argtypes = [c_f]
         lib.oracle_to_fixed.restype = C.c_int64
+        lib.oracle_make_rays.argtypes = [C.c_int, vp, C.POINTER(RenderParams), vp, vp, c_u32, c_u64, vp, vp]
         self._bind_funcs(lib, "oracle_")
 
     def scene(self, world_ptr, root_ptr):
         return OracleScene(self, world_ptr, root_ptr)
+
+    def make_camera_rays(self, camera_ptr, params, seed, n):
+        """BASELINE config 2, coherent buffer: n lens-sampled primaries of the params' grid (xorshift streams of `seed`)"""
+        o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32)
+        self.lib.oracle_make_rays(0, camera_ptr, C.byref(params), None, None, seed, n, _ptr(o), _ptr(d))
+        return o, d
+
+    def make_random_rays(self, box_min, box_max, seed, n):
+        """BASELINE config 2, incoherent buffer: origins uniform in the box, directions uniform on the sphere"""
+        o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32)
+        lo, hi = f32a(box_min), f32a(box_max)
+        self.lib.oracle_make_rays(1, None, None, _ptr(lo), _ptr(hi), seed, n, _ptr(o), _ptr(d))
+        return o, d
 
 
 class OracleScene:
