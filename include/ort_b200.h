@@ -250,8 +250,8 @@ typedef struct OrtRenderStats
     uint32_t kernel_launches;  /* kernels launched by this call */
     float    extend_ms;        /* wavefront: summed CUDA-event time of the EXTEND launches */
     float    shade_ms;         /* wavefront: ... of the SHADE launches */
-    float    sort_ms;          /* wavefront: ... of the key scan + scatter launches */
-    uint32_t reserved;
+    float    sort_ms;          /* wavefront: 0 -- the class sort runs inside SHADE, tile by tile, since round 2 */
+    uint32_t extend_launches;  /* wavefront: number of EXTEND launches of this call */
 } OrtRenderStats;
 
 void ort_render_params_default(OrtRenderParams *params, int32_t width, int32_t height,

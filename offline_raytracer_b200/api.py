@@ -58,7 +58,7 @@ class RenderParams(C.Structure):
 class RenderStats(C.Structure):
     _fields_ = [("samples", c_u64), ("rays", c_u64), ("node_visits", c_u64), ("box_tests", c_u64),
                 ("shape_tests", c_u64), ("device_ms", c_f), ("kernel_launches", c_u32),
-                ("extend_ms", c_f), ("shade_ms", c_f), ("sort_ms", c_f), ("reserved", c_u32)]
+                ("extend_ms", c_f), ("shade_ms", c_f), ("sort_ms", c_f), ("extend_launches", c_u32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -95,6 +95,7 @@ struct SceneView
     // triangles from tri_root.
     uint32_t main_root;
     uint32_t tri_root;
+    const uint8_t *mat_class;  // per material: is_light << 3 | lobes (the wavefront's shading class; unused elsewhere)
 };
 
 struct TraceCounters { uint32_t node_visits, box_tests, shape_tests; };
@@ -163,6 +164,15 @@ ORT_HD float byte_f_xu(uint32_t w, uint32_t k) { return (float)((w >> (8u * k)) 
 #define ORT_I2F_PLANES 5
 #endif
 
+// packed f32x2 FMA for the slab test (sm_100: fma.rn.f32x2); the host build keeps the scalar form
+#ifndef ORT_SLAB_FMA2
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+#define ORT_SLAB_FMA2 1
+#else
+#define ORT_SLAB_FMA2 0
+#endif
+#endif
+
 // traversal stack of pending node groups: a per-thread array here; the wavefront extend
 // kernel substitutes a shared-memory column (wavefront.cuh)
 struct LocalStack
@@ -182,6 +192,36 @@ struct Trav
     float best_t;
     uint32_t best_prim, best_rank;
 };
+
+// what a node visit needs to know about the ray: origin, the reciprocal direction of the (conservative)
+// slab tests -- the exact one, except that zero and denormal-small components are clamped so that
+// 0 * inf never appears and (p - o) * id cannot overflow -- and the sign octant
+struct SlabConsts { float ox, oy, oz, idx, idy, idz; uint32_t octinv; };
+#define ORT_SLAB_TINY 1e-20f
+#define ORT_SLAB_HUGE 1e20f
+ORT_HD SlabConsts make_slab_consts(f3 o, f3 d, f3 inv)
+{
+    SlabConsts c;
+    c.ox = o.x; c.oy = o.y; c.oz = o.z;
+    c.idx = fabsf(d.x) > ORT_SLAB_TINY ? inv.x : (f2u(d.x) >> 31 ? -ORT_SLAB_HUGE : ORT_SLAB_HUGE);
+    c.idy = fabsf(d.y) > ORT_SLAB_TINY ? inv.y : (f2u(d.y) >> 31 ? -ORT_SLAB_HUGE : ORT_SLAB_HUGE);
+    c.idz = fabsf(d.z) > ORT_SLAB_TINY ? inv.z : (f2u(d.z) >> 31 ? -ORT_SLAB_HUGE : ORT_SLAB_HUGE);
+    c.octinv = 7u - ((c.idx < 0.0f ? 1u : 0u) | (c.idy < 0.0f ? 2u : 0u) | (c.idz < 0.0f ? 4u : 0u));
+    return c;
+}
+ORT_HD SlabConsts slab_consts(const Trav &t) { return make_slab_consts(t.o, t.d, t.inv); }
+
+template <class T, class Stack>
+ORT_HD void trav_init_state(const SceneView &s, T &t, Stack &st)
+{
+    t.best_t = FLT_MAX; t.best_prim = 0xFFFFFFFFu; t.best_rank = 0xFFFFFFFFu;
+    // node group: a root as the single hit child of a virtual parent (imask 0 => relative index 0).
+    // Order: analytic shapes (their hit clips what follows), triangles, spheres (unclipped).
+    t.ng_x = s.main_root; t.ng_y = 0x80000000u;
+    t.sp = 0;
+    if(s.main_root != 0u) { st.put(t.sp, 0u, 0x80000000u); ++t.sp; }
+    if(s.tri_root != s.main_root) { st.put(t.sp, s.tri_root, 0x80000000u); ++t.sp; }
+}
 
 template <class Stack>
 ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
@@ -204,18 +244,14 @@ ORT_HD void trav_init(const SceneView &s, Trav &t, Stack &st, f3 o, f3 d)
 // applies: nodes below main_root -- the sphere tree -- are never clipped).
 // COUNT: 0 = no counters, 1 = all three (the counters build), 2 = primitive tests only (the product
 // build: the reference's entry point returns that tally, ray.cpp:661-715, 1173)
-template <int COUNT, class Stack>
-ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, TraceCounters *cnt,
+template <int COUNT, class T, class Stack>
+ORT_HD void trav_visit(const SceneView &s, T &t, Stack &st, float clip_t, TraceCounters *cnt,
                        uint32_t *tg_x_out, uint32_t *tg_y_out, uint32_t *node_index_out, uint32_t *mixed_out = 0)
 {
-    // reciprocal direction of the (conservative) slab tests: the exact one, except that zero and
-    // denormal-small components are clamped so that 0 * inf never appears
-    const float tiny = 1e-20f, huge = 1e20f;
-    const float idx = fabsf(t.d.x) > tiny ? t.inv.x : (f2u(t.d.x) >> 31 ? -huge : huge);
-    const float idy = fabsf(t.d.y) > tiny ? t.inv.y : (f2u(t.d.y) >> 31 ? -huge : huge);
-    const float idz = fabsf(t.d.z) > tiny ? t.inv.z : (f2u(t.d.z) >> 31 ? -huge : huge);
-    const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
-    const uint32_t octinv = 7u - ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
+    const SlabConsts rc = slab_consts(t);
+    const float idx = rc.idx, idy = rc.idy, idz = rc.idz;
+    const uint32_t octinv = rc.octinv;
+    const bool nx = ((7u - octinv) & 1u) != 0u, ny = ((7u - octinv) & 2u) != 0u, nz = ((7u - octinv) & 4u) != 0u;
 
     uint32_t bit = msb32(t.ng_y);
     uint32_t hits_imask = t.ng_y;
@@ -236,13 +272,21 @@ ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, Tra
     float ax = u2f((e_imask & 0xFFu) << 23) * idx;
     float ay = u2f(((e_imask >> 8) & 0xFFu) << 23) * idy;
     float az = u2f(((e_imask >> 16) & 0xFFu) << 23) * idz;
-    float bx = (n0.x - t.o.x) * idx;
-    float by = (n0.y - t.o.y) * idy;
-    float bz = (n0.z - t.o.z) * idz;
+    float bx = (n0.x - rc.ox) * idx;
+    float by = (n0.y - rc.oy) * idy;
+    float bz = (n0.z - rc.oz) * idz;
 
     t.ng_x = f2u(n1.x);
     uint32_t hitmask = 0u;
     const uint32_t octinv4 = octinv * 0x01010101u;
+#if ORT_SLAB_FMA2
+    // Blackwell's packed FP32 pipe: the six plane distances of TWO children are three fma.rn.f32x2
+    // pairs per side -- (x, y) of child k, (x, y) of child k + 1, (z of k, z of k + 1) -- i.e. 24
+    // issue slots per node instead of 48.  Each half of an f32x2 FMA rounds exactly like the scalar
+    // fmaf, so the hit masks (and the host build, which keeps the scalar form) are unchanged.
+    const float2 a_xy = make_float2(ax, ay), b_xy = make_float2(bx, by);
+    const float2 a_zz = make_float2(az, az), b_zz = make_float2(bz, bz);
+#endif
 #pragma unroll
     for(int half = 0; half < 2; ++half)
     {
@@ -262,6 +306,31 @@ ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, Tra
         uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
         uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
         uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#if ORT_SLAB_FMA2
+#pragma unroll
+        for(uint32_t k = 0; k < 4; k += 2)
+        {
+            float2 n0 = __ffma2_rn(make_float2(ORT_I2F_PLANES >= 6 ? byte_f_xu(nearx, k) : byte_f(nearx, k),
+                                               ORT_I2F_PLANES >= 5 ? byte_f_xu(neary, k) : byte_f(neary, k)), a_xy, b_xy);
+            float2 n1_ = __ffma2_rn(make_float2(ORT_I2F_PLANES >= 6 ? byte_f_xu(nearx, k + 1) : byte_f(nearx, k + 1),
+                                                ORT_I2F_PLANES >= 5 ? byte_f_xu(neary, k + 1) : byte_f(neary, k + 1)), a_xy, b_xy);
+            float2 nz2 = __ffma2_rn(make_float2(ORT_I2F_PLANES >= 4 ? byte_f_xu(nearz, k) : byte_f(nearz, k),
+                                                ORT_I2F_PLANES >= 4 ? byte_f_xu(nearz, k + 1) : byte_f(nearz, k + 1)), a_zz, b_zz);
+            float2 f0 = __ffma2_rn(make_float2(ORT_I2F_PLANES >= 3 ? byte_f_xu(farx, k) : byte_f(farx, k),
+                                               ORT_I2F_PLANES >= 2 ? byte_f_xu(fary, k) : byte_f(fary, k)), a_xy, b_xy);
+            float2 f1 = __ffma2_rn(make_float2(ORT_I2F_PLANES >= 3 ? byte_f_xu(farx, k + 1) : byte_f(farx, k + 1),
+                                               ORT_I2F_PLANES >= 2 ? byte_f_xu(fary, k + 1) : byte_f(fary, k + 1)), a_xy, b_xy);
+            float2 fz2 = __ffma2_rn(make_float2(ORT_I2F_PLANES >= 1 ? byte_f_xu(farz, k) : byte_f(farz, k),
+                                                ORT_I2F_PLANES >= 1 ? byte_f_xu(farz, k + 1) : byte_f(farz, k + 1)), a_zz, b_zz);
+            float tmin0 = fmaxf(fmaxf(n0.x, n0.y), fmaxf(nz2.x, 0.0f)), tmax0 = fminf(fminf(f0.x, f0.y), fminf(fz2.x, t_clip));
+            float tmin1 = fmaxf(fmaxf(n1_.x, n1_.y), fmaxf(nz2.y, 0.0f)), tmax1 = fminf(fminf(f1.x, f1.y), fminf(fz2.y, t_clip));
+            if(COUNT == 1) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; if((meta4 >> (8u * (k + 1u))) & 0xFFu) cnt->box_tests++; }
+            uint32_t cb0 = (child_bits4 >> (8u * k)) & 0xFFu, bi0 = (bit_index4 >> (8u * k)) & 0xFFu;
+            uint32_t cb1 = (child_bits4 >> (8u * (k + 1u))) & 0xFFu, bi1 = (bit_index4 >> (8u * (k + 1u))) & 0xFFu;
+            hitmask |= (tmin0 <= tmax0) ? (cb0 << bi0) : 0u;
+            hitmask |= (tmin1 <= tmax1) ? (cb1 << bi1) : 0u;
+        }
+#else
 #pragma unroll
         for(uint32_t k = 0; k < 4; ++k)
         {
@@ -278,6 +347,7 @@ ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, Tra
             uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
             hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
         }
+#endif
     }
     t.ng_y = (hitmask & 0xFF000000u) | (e_imask >> 24);
     *tg_x_out = f2u(n1.y) & ~ORT_NODE_MIXED_KINDS;
@@ -287,8 +357,8 @@ ORT_HD void trav_visit(const SceneView &s, Trav &t, Stack &st, float clip_t, Tra
 }
 
 // Pops the next pending node group when the current one is exhausted; false = traversal done.
-template <class Stack>
-ORT_HD bool trav_next(Trav &t, Stack &st)
+template <class T, class Stack>
+ORT_HD bool trav_next(T &t, Stack &st)
 {
     if(t.ng_y & 0xFF000000u) return true;
     if(t.sp == 0) return false;

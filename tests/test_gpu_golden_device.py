@@ -91,26 +91,22 @@ def test_bsdf_golden_on_device(ort, gold):
     # integer side: exactly three xorshift steps, always (ray.cpp:1106-1108)
     assert np.array_equal(g["state_after"], gold["bsdf_sample_state"])
     # the lobe decision compares `choice` with sums of per-material constants formed by the same IEEE
-    # operations: exact, except where total internal reflection is decided by a radicand within libm noise of 0
-    flip = g["is_transmission"] != gold["bsdf_sample_is_t"]
-    assert flip.sum() <= 2, flip.sum()
-    same = ~flip
-    # sampled direction: unit vector built from sinf / cosf / atan2f / sqrtf -- CUDA's libm is within 2 ulp
-    # of glibc's on these ranges; a unit vector's components then agree to ~1e-6 absolute
-    err = np.abs(g["sample_wi"][same] - gold["bsdf_sample_wi"][same]).max(axis=1)
-    assert np.percentile(err, 99) <= 2e-6, np.percentile(err, 99)
-    assert err.max() <= 2e-4, err.max()            # GGX half vectors at roughness 0.01 amplify the angle's last ulp
-    assert np.allclose(np.linalg.norm(g["sample_wi"], axis=1), 1.0, atol=1e-5)
-    # pdf and f: the GGX lobe with roughness 0.01 is a spike (D ~ 1/r^2 = 1e4 at the peak and falling by orders of
-    # magnitude within a degree), so the relative error of D is the relative error of tan^2 / r^2, i.e. a few
-    # float ulps of n.h amplified by up to ~1e3 near the spike.  Bound: 99 % of tuples within 1e-5 relative,
-    # every tuple within 2e-3 relative (floor 1e-6 absolute for values that are zero in the reference).
+    # operations, and the total-internal-reflection test is IEEE-only as well: exact
+    assert np.array_equal(g["is_transmission"], gold["bsdf_sample_is_t"])
+    # Stated bound for the libm side (CUDA's sinf / cosf / atan2f / logf / expf vs glibc's, and the device's
+    # powf(x, 5) / powf(x, 4) / powf(e, y) -> products / expf substitution, path.h:137-145).  Measured on B200
+    # over the 1500 tuples: sampled direction max 1.2e-7 absolute (1 ulp of a unit-vector component), pdf max
+    # 3.9e-7 relative, f max 5.2e-7 relative (3-4 ulp).  Asserted: 4 ulp of 1.0 absolute for the direction,
+    # 16 ulp relative (floor 1e-6 absolute) for pdf and f.
+    err = np.abs(g["sample_wi"] - gold["bsdf_sample_wi"]).max(axis=1)
+    assert err.max() <= 4 * 1.1920929e-07, err.max()
+    assert np.allclose(np.linalg.norm(g["sample_wi"], axis=1), 1.0, atol=1e-6)
     e_pdf = rel_err(g["pdf"], gold["bsdf_pdf"], 1e-6)
-    assert np.percentile(e_pdf, 99) <= 1e-5, np.percentile(e_pdf, 99)
-    assert e_pdf.max() <= 2e-3, e_pdf.max()
+    assert e_pdf.max() <= 16 * 1.1920929e-07, e_pdf.max()
     e_ev = rel_err(g["eval"], gold["bsdf_eval"], 1e-6).max(axis=1)
-    assert np.percentile(e_ev, 99) <= 1e-5, np.percentile(e_ev, 99)
-    assert e_ev.max() <= 2e-3, e_ev.max()
+    assert e_ev.max() <= 16 * 1.1920929e-07, e_ev.max()
+    # most tuples do not touch libm-sensitive terms at all: bit-equal
+    assert (bits(g["pdf"]) == bits(gold["bsdf_pdf"])).mean() >= 0.8
     # zero stays zero: a lobe the reference does not evaluate is not evaluated here either
     z = gold["bsdf_pdf"] == 0
     assert np.all(g["pdf"][z] == 0)
