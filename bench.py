@@ -315,7 +315,7 @@ def roofline_objects(key, cfg, info, st, per_ray, peaks):
     rays, kernel_ms = st["rays"], st["device_ms"]
     wavefront = st["extend_ms"] > 0
     extend_ms = st["extend_ms"] if wavefront else kernel_ms
-    n_launch = max(1, (st["kernel_launches"] - 2) // 4) if wavefront else 1
+    n_launch = max(1, st.get("extend_launches", 0)) if wavefront else 1
     rps = rays / (extend_ms * 1e-3)
     bytes_per_ray = 48.0 * per_ray["shape_tests"] + info["bvh_node_bytes"] * per_ray["node_visits"]
     flops_per_ray = 51.0 * per_ray["shape_tests"] + 25.0 * per_ray["box_tests"]

@@ -250,7 +250,7 @@ typedef struct OrtRenderStats
     uint32_t kernel_launches;  /* kernels launched by this call */
     float    extend_ms;        /* wavefront: summed CUDA-event time of the EXTEND launches */
     float    shade_ms;         /* wavefront: ... of the SHADE launches */
-    float    sort_ms;          /* wavefront: 0 -- the class sort runs inside SHADE, tile by tile, since round 2 */
+    float    sort_ms;          /* wavefront: ... of the key scan + scatter launches */
     uint32_t extend_launches;  /* wavefront: number of EXTEND launches of this call */
 } OrtRenderStats;
 
@@ -400,6 +400,14 @@ const OrtMesh *ort_host_scene_meshes(const OrtHostScene *hs, uint32_t *mesh_coun
  * makes ort_host_scene_load skip the octree (ort_host_scene_root then returns NULL) */
 #define ORT_HOST_NO_OCTREE 2
 int ort_host_scene_lists(const OrtHostScene *hs, OrtShapeLists *out);
+/* Mesh bake on the device.  Replaces the per-vertex loop of main() (code/macos_main.mm:382-413):
+ * v *= scale; rotate by `degree` about (0, 1, 0); rotate by `quaternion`; v += translate -- and the mesh AABB folded
+ * from (FLT_MAX, FLT_MIN) as the reference does (FLT_MIN = smallest positive float: a mesh in negative space keeps
+ * a max of 1.2e-38).  Host pointers; in and out may be the same array.  Baked vertices and the box are bit-identical
+ * to the host bake (tests/test_gpu_build.py).  ort_host_scene_load uses it when with_csg has ORT_HOST_BAKE_ON_DEVICE. */
+int ort_bake_mesh(int device, uint32_t vertex_count, const ort_v3 *vertices_in, ort_v3 *vertices_out,
+                  float scale, float degree, ort_v4 quaternion, ort_v3 translate, ort_v3 *aabb_min, ort_v3 *aabb_max);
+#define ORT_HOST_BAKE_ON_DEVICE 4
 /* mesh loader alone; vertices (xyz floats) and indices are malloc'd, free with ort_free */
 int ort_load_mesh(const char *path, float **vertices, uint32_t *vertex_count,
                   uint32_t **indices, uint32_t *index_count);

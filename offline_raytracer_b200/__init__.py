@@ -8,5 +8,5 @@ from .api import (  # noqa: F401
     OrtError, Camera, RenderParams, RenderStats, Scene, HostScene,
     default_params, device_count, lib, load_mesh, parse_numeric, write_hdr, v3_to_rgbe,
     measure_fp32_peak, measure_l2_bandwidth, selftest_div3, selftest_intersect, selftest_bsdf,
-    generate_camera_rays_device, generate_random_rays_device, Multi, Progress, LIB_PATH, ORT_BUILD_ON_DEVICE, ORT_HOST_NO_OCTREE, ShapeLists,
+    generate_camera_rays_device, generate_random_rays_device, Multi, Progress, bake_mesh, LIB_PATH, ORT_BUILD_ON_DEVICE, ORT_HOST_NO_OCTREE, ShapeLists,
 )

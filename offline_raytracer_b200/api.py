@@ -85,6 +85,17 @@ class ShapeLists(C.Structure):
 
 
 ORT_HOST_NO_OCTREE = 2
+ORT_HOST_BAKE_ON_DEVICE = 4
+
+
+class V4(C.Structure):
+    _fields_ = [("x", c_f), ("y", c_f), ("z", c_f), ("w", c_f)]
+
+
+class Mesh(C.Structure):
+    """OrtMesh == reference Mesh (code/ray.h:51-65)"""
+    _fields_ = [("vertices", vp), ("vertex_count", c_u32), ("indices", vp), ("index_count", c_u32), ("mat_index", c_u32),
+                ("aabb_min", c_f * 3), ("aabb_max", c_f * 3)]
 
 
 class BuildStats(C.Structure):
@@ -138,6 +149,7 @@ def lib(path=None):
     L.ort_raycast_brute_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp]
     L.ort_raycast_counters_device.argtypes = [vp, c_u64, vp, vp, C.POINTER(c_u64), C.POINTER(c_u64), C.POINTER(c_u64)]
     L.ort_scene_device.argtypes = [vp, C.POINTER(C.c_int)]
+    L.ort_bake_mesh.argtypes = [C.c_int, c_u32, vp, vp, c_f, c_f, V4, V3, C.POINTER(V3), C.POINTER(V3)]
     L.ort_measure_l2_bandwidth.argtypes = [C.c_int, c_u32, C.POINTER(c_f)]
     L.ort_selftest_intersect.argtypes = [C.c_int, c_u32, c_u32, vp, vp]
     L.ort_selftest_bsdf.argtypes = [C.c_int, c_u32, vp, vp, vp, vp, vp, vp, c_f, vp, vp, vp, vp, vp]
@@ -292,13 +304,14 @@ class HostScene:
         self.root = L.ort_host_scene_root(handle)
 
     @classmethod
-    def load(cls, scn_path, base_dir, width, height, with_csg=True, octree=True):
-        """octree=False skips the reference's octree (root is then None): for Scene.from_lists"""
+    def load(cls, scn_path, base_dir, width, height, with_csg=True, octree=True, bake_on_device=False):
+        """octree=False skips the reference's octree (root is then None): for Scene.from_lists;
+        bake_on_device=True runs the mesh bake (macos_main.mm:382-413) as a CUDA kernel (ort_bake_mesh)"""
         L = lib()
         if not base_dir.endswith("/"):
             base_dir += "/"
         h = vp(0)
-        flags = (1 if with_csg else 0) | (0 if octree else ORT_HOST_NO_OCTREE)
+        flags = (1 if with_csg else 0) | (0 if octree else ORT_HOST_NO_OCTREE) | (ORT_HOST_BAKE_ON_DEVICE if bake_on_device else 0)
         _check(L.ort_host_scene_load(scn_path.encode(), base_dir.encode(), width, height, flags, C.byref(h)))
         return cls(h, width, height)
 
@@ -312,6 +325,19 @@ class HostScene:
 
     def camera_array(self):
         return np.ctypeslib.as_array(C.cast(self.camera, C.POINTER(c_f)), shape=(12,)).copy()
+
+    def meshes(self):
+        """[(vertices [n, 3] float32 copy, indices copy, aabb_min, aabb_max, mat_index)] of the baked meshes"""
+        n = c_u32(0)
+        p = lib().ort_host_scene_meshes(self.h, C.byref(n))
+        arr = C.cast(p, C.POINTER(Mesh))
+        out = []
+        for i in range(n.value):
+            m = arr[i]
+            v = np.ctypeslib.as_array(C.cast(m.vertices, C.POINTER(c_f)), shape=(m.vertex_count * 3,)).copy().reshape(-1, 3)
+            idx = np.ctypeslib.as_array(C.cast(m.indices, C.POINTER(c_u32)), shape=(m.index_count,)).copy()
+            out.append((v, idx, np.array(list(m.aabb_min), np.float32), np.array(list(m.aabb_max), np.float32), m.mat_index))
+        return out
 
     def close(self):
         if self.h:
@@ -573,6 +599,16 @@ class Progress:
         if self.h:
             self.L.ort_progress_destroy(self.h)
             self.h = None
+
+
+def bake_mesh(vertices, scale, degree, quaternion_xyzw, translate, device=0):
+    """ort_bake_mesh: (baked vertices [n, 3], aabb_min, aabb_max) -- the reference's mesh bake as a CUDA kernel"""
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    out = np.zeros_like(v)
+    mn, mx = V3(), V3()
+    q = V4(*[float(x) for x in quaternion_xyzw]); t = V3(*[float(x) for x in translate])
+    _check(lib().ort_bake_mesh(device, v.shape[0], _ptr(v), _ptr(out), c_f(scale), c_f(degree), q, t, C.byref(mn), C.byref(mx)))
+    return out, np.array([mn.x, mn.y, mn.z], np.float32), np.array([mx.x, mx.y, mx.z], np.float32)
 
 
 def load_mesh(path):

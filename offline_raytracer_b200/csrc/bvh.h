@@ -95,7 +95,6 @@ struct SceneView
     // triangles from tri_root.
     uint32_t main_root;
     uint32_t tri_root;
-    const uint8_t *mat_class;  // per material: is_light << 3 | lobes (the wavefront's shading class; unused elsewhere)
 };
 
 struct TraceCounters { uint32_t node_visits, box_tests, shape_tests; };

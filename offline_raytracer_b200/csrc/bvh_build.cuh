@@ -58,6 +58,14 @@ __global__ void k_ploc_apply(uint32_t n, const uint32_t *__restrict__ nn, const 
 }
 
 // the clusters still alive: their nodes, sizes and costs, packed for the host's top-tree build
+// the four numbers the host needs after a round (the last element of two exclusive scans and of their inputs),
+// gathered into one 16-byte record so that a round costs ONE device-to-host copy instead of four blocking ones
+__global__ void k_tail4(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, const uint32_t *__restrict__ c,
+                        const uint32_t *__restrict__ d, uint32_t last, uint32_t *__restrict__ out)
+{
+    if(threadIdx.x == 0) { out[0] = a[last]; out[1] = b[last]; out[2] = c[last]; out[3] = d[last]; }
+}
+
 __global__ void k_pack_clusters(uint32_t count, const uint32_t *__restrict__ cluster, const B2 *__restrict__ nodes,
                                 const uint32_t *__restrict__ sizes, const Dp *__restrict__ cost, B2 *out_nodes, uint32_t *out_sizes, Dp *out_cost)
 {
@@ -125,6 +133,7 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
     uint32_t *d_cluster = 0, *d_cluster2 = 0, *d_nn = 0, *d_fate = 0, *d_keep = 0, *d_merge = 0, *d_pos = 0, *d_mid = 0;
     WideNode *d_wide = 0; Item *d_items = 0, *d_items2 = 0; Kids *d_kids = 0;
     void *d_temp = 0; size_t temp_bytes = 0;
+    uint32_t *d_tail = 0;
     cudaEvent_t e0 = 0, e1 = 0;
     uint32_t wide_cap = 0, node_count = 0, prim_count = 0, depth = 0, iterations = 0;
     D3 lo, sc;
@@ -172,6 +181,7 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
             cub::DeviceScan::ExclusiveSum((void *)0, b, d_keep, d_pos, (int)n);
             temp_bytes = (a > b ? a : b) + 256;
             BUILD_TRY(cudaMalloc(&d_temp, temp_bytes));
+            BUILD_TRY(cudaMalloc((void **)&d_tail, 16));
         }
         if(!d_boxes_in)
         {
@@ -199,10 +209,8 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
                 k_ploc_apply<<<G(count), T>>>(count, d_nn, d_cluster, d_fate, d_pos, d_mid, next_node, d_b2, d_sizes, d_cost, d_cluster2,
                                                in.max_leaf, in.node_cost);
                 uint32_t last[4];
-                BUILD_TRY(cudaMemcpy(&last[0], d_pos + (count - 1), 4, cudaMemcpyDeviceToHost));
-                BUILD_TRY(cudaMemcpy(&last[1], d_keep + (count - 1), 4, cudaMemcpyDeviceToHost));
-                BUILD_TRY(cudaMemcpy(&last[2], d_mid + (count - 1), 4, cudaMemcpyDeviceToHost));
-                BUILD_TRY(cudaMemcpy(&last[3], d_merge + (count - 1), 4, cudaMemcpyDeviceToHost));
+                k_tail4<<<1, 32>>>(d_pos, d_keep, d_mid, d_merge, count - 1, d_tail);
+                BUILD_TRY(cudaMemcpy(last, d_tail, 16, cudaMemcpyDeviceToHost));
                 uint32_t kept = last[0] + last[1], merged = last[2] + last[3];
                 if(merged == 0 || kept >= count) { *err = "internal: PLOC made no progress"; ok = false; goto done; }
                 next_node += merged; count = kept;
@@ -258,10 +266,8 @@ inline bool build_on_device(const FlatScene &flat, const ParallelBuildInput &in,
                 tb = temp_bytes;
                 BUILD_TRY(cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nprims, d_poff, (int)n_items));
                 uint32_t last[4];
-                BUILD_TRY(cudaMemcpy(&last[0], d_ioff + (n_items - 1), 4, cudaMemcpyDeviceToHost));
-                BUILD_TRY(cudaMemcpy(&last[1], d_ninner + (n_items - 1), 4, cudaMemcpyDeviceToHost));
-                BUILD_TRY(cudaMemcpy(&last[2], d_poff + (n_items - 1), 4, cudaMemcpyDeviceToHost));
-                BUILD_TRY(cudaMemcpy(&last[3], d_nprims + (n_items - 1), 4, cudaMemcpyDeviceToHost));
+                k_tail4<<<1, 32>>>(d_ioff, d_ninner, d_poff, d_nprims, n_items - 1, d_tail);
+                BUILD_TRY(cudaMemcpy(last, d_tail, 16, cudaMemcpyDeviceToHost));
                 uint32_t total_inner = last[0] + last[1], total_prims = last[2] + last[3];
                 if(node_count - node_offset + total_inner > wide_cap + 1u || total_inner > wide_cap) { *err = "internal: wide node bound exceeded"; ok = false; goto done; }
                 k_emit<<<G(n_items), T>>>(n_items, d_items, d_kids, d_ioff, d_poff, node_count, prim_count, d_b2, d_sizes, in.max_leaf,
@@ -289,7 +295,7 @@ done:
     cudaFree(d_codes); cudaFree(d_codes2); cudaFree(d_idx); cudaFree(d_order);
     cudaFree(d_b2); cudaFree(d_sizes); cudaFree(d_cost); cudaFree(d_cluster); cudaFree(d_cluster2); cudaFree(d_nn); cudaFree(d_fate);
     cudaFree(d_keep); cudaFree(d_merge); cudaFree(d_pos); cudaFree(d_mid); cudaFree(d_wide); cudaFree(d_items); cudaFree(d_items2);
-    cudaFree(d_kids); cudaFree(d_temp);
+    cudaFree(d_kids); cudaFree(d_temp); cudaFree(d_tail);
     if(e0) cudaEventDestroy(e0);
     if(e1) cudaEventDestroy(e1);
     if(!ok)
@@ -336,8 +342,10 @@ __global__ void k_tri_codes(uint32_t n_tri, MeshTable mt, const float *__restric
         load_triangle(mt, verts, idx, i, &a, &b, &c, &mat);
         keys[i] = octant_path(triangle_centre(a, b, c), root_center, root_half);
         who[i] = i;
-        m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fabsf(a.z)), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fabsf(b.z)));
-        m = fmaxf(m, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fabsf(c.z)));
+        // fmaxf drops NaNs: map them to +Inf first, so that the host sees a non-finite maximum and rejects the mesh
+        auto mag = [](float v) { return v == v ? fabsf(v) : __int_as_float(0x7F800000); };
+        m = fmaxf(fmaxf(fmaxf(mag(a.x), mag(a.y)), mag(a.z)), fmaxf(fmaxf(mag(b.x), mag(b.y)), mag(b.z)));
+        m = fmaxf(m, fmaxf(fmaxf(mag(c.x), mag(c.y)), mag(c.z)));
     }
     for(int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xFFFFFFFFu, m, o));
     if((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax_bits, __float_as_uint(m));      // non-negative floats order like their bits
@@ -580,6 +588,8 @@ inline bool records_from_lists_on_device(const OrtWorld *world, const OrtShapeLi
     flat->info.root_min[0] = L->root_min.x; flat->info.root_min[1] = L->root_min.y; flat->info.root_min[2] = L->root_min.z;
     flat->info.root_max[0] = L->root_max.x; flat->info.root_max[1] = L->root_max.y; flat->info.root_max[2] = L->root_max.z;
     if(fill_world_tables_public(world, flat, err) != ORT_OK) { ok = false; goto done; }
+    // |v| of every mesh vertex was folded with an unsigned max of its bits: Inf and NaN (exponent all ones) end up on top
+    if(absmax_bits >= 0x7F800000u) { *err = "mesh with non-finite vertices (NaN / Inf)"; ok = false; goto done; }
     { float m; memcpy(&m, &absmax_bits, 4); scene_abs = (double)m; }
     for(size_t k = 0; k < analytic.size(); ++k)
     {

@@ -160,6 +160,9 @@ int load_ply(const uint8_t *mem, size_t size, std::vector<ort_v3> *vertices, std
             {
                 PlyToken n = ply_token(c);
                 if(n.type != PLY_I32) { *err = "ply: element vertex without a count"; return ORT_ERR_PARSE; }
+                // an ASCII vertex line is at least "0 0 0\n" = 6 bytes: a count the file cannot hold is a parse error,
+                // not an allocation
+                if(n.num.i < 0 || (uint64_t)n.num.i > (uint64_t)size / 6u + 1u) { *err = "ply: vertex count does not fit the file"; return ORT_ERR_PARSE; }
                 vertex_count = (uint32_t)n.num.i;
             }
             else if(name.type != PLY_FACE) { *err = "ply: unsupported element"; return ORT_ERR_PARSE; }
@@ -191,6 +194,8 @@ int load_ply(const uint8_t *mem, size_t size, std::vector<ort_v3> *vertices, std
         if(ply_token(peek).type == PLY_NULL) break;
         PlyToken n = ply_token(c);
         if(n.type != PLY_I32 || n.num.i < 3) { *err = "ply: malformed face line"; return ORT_ERR_PARSE; }
+        // every index of the face takes at least two bytes of the file ("0 ")
+        if((uint64_t)n.num.i > (uint64_t)(c.end - c.at) / 2u + 1u) { *err = "ply: face arity does not fit the file"; return ORT_ERR_PARSE; }
         PlyToken a = ply_token(c), b = ply_token(c), d = ply_token(c);
         if(a.type != PLY_I32 || b.type != PLY_I32 || d.type != PLY_I32) { *err = "ply: malformed face indices"; return ORT_ERR_PARSE; }
         indices->push_back((uint32_t)a.num.i); indices->push_back((uint32_t)b.num.i); indices->push_back((uint32_t)d.num.i);
@@ -198,6 +203,7 @@ int load_ply(const uint8_t *mem, size_t size, std::vector<ort_v3> *vertices, std
         {
             uint32_t second = indices->back();
             PlyToken e = ply_token(c);
+            if(e.type != PLY_I32) { *err = "ply: malformed face indices"; return ORT_ERR_PARSE; }
             indices->push_back((uint32_t)a.num.i); indices->push_back(second); indices->push_back((uint32_t)e.num.i);
         }
     }

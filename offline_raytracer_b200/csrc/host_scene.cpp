@@ -23,6 +23,8 @@
 #include <string>
 #include <utility>
 
+#include <new>
+#include <stdexcept>
 #include "core_math.h"
 
 namespace ort {
@@ -279,6 +281,7 @@ int assemble_scene(const char *scn_path, const char *base_dir, int32_t width, in
 
     // hard-coded, inert CSG (macos_main.mm:322-332); it occupies a rank
     const bool build_octree = (with_csg & ORT_HOST_NO_OCTREE) == 0;
+    const bool bake_on_device = (with_csg & ORT_HOST_BAKE_ON_DEVICE) != 0;
     hs->has_csg = (with_csg & 1) != 0;
     memset(&hs->csg, 0, sizeof(hs->csg));
     if(hs->has_csg)
@@ -349,6 +352,14 @@ int assemble_scene(const char *scn_path, const char *base_dir, int32_t width, in
         for(size_t k = 0; k < hs->mesh_indices[mi].size(); ++k)
             if(hs->mesh_indices[mi][k] >= mesh.vertex_count) { *err = "mesh index out of range: " + info.file_path; return ORT_ERR_PARSE; }
 
+        if(bake_on_device)
+        {
+            // the same loop as a CUDA kernel (ort_tools.cu: k_bake_mesh), bit-identical vertices and box
+            int brc = ort_bake_mesh(0, mesh.vertex_count, mesh.vertices, mesh.vertices, info.scale, info.degree,
+                                    info.quaternion, info.translate, &mesh.aabb_min, &mesh.aabb_max);
+            if(brc != ORT_OK) { *err = std::string("device bake: ") + ort_last_error(); return brc; }
+            continue;
+        }
         f3 mn = mk3(FLT_MAX, FLT_MAX, FLT_MAX);
         f3 mx = mk3(FLT_MIN, FLT_MIN, FLT_MIN);
         for(uint32_t vi = 0; vi < mesh.vertex_count; ++vi)
@@ -491,10 +502,17 @@ int ort_host_scene_load(const char *scn_path, const char *base_dir, int32_t widt
 {
     if(!scn_path || !base_dir || !out) { ort_set_last_error_("null argument"); return ORT_ERR_ARG; }
     *out = 0;
-    OrtHostScene *hs = new OrtHostScene();
-    std::string err;
-    int rc = ort::assemble_scene(scn_path, base_dir, width, height, with_csg, hs, &err);
-    if(rc != ORT_OK) { ort_set_last_error_(err.c_str()); delete hs; return rc; }
+    OrtHostScene *hs = 0;
+    // no C++ exception crosses the C ABI: a file that makes a container throw is a reported error, not std::terminate
+    try
+    {
+        hs = new OrtHostScene();
+        std::string err;
+        int rc = ort::assemble_scene(scn_path, base_dir, width, height, with_csg, hs, &err);
+        if(rc != ORT_OK) { ort_set_last_error_(err.c_str()); delete hs; return rc; }
+    }
+    catch(const std::bad_alloc &) { delete hs; ort_set_last_error_("out of host memory while loading the scene"); return ORT_ERR_LIMIT; }
+    catch(const std::exception &e) { delete hs; ort_set_last_error_((std::string("scene loader: ") + e.what()).c_str()); return ORT_ERR_PARSE; }
     *out = hs;
     return ORT_OK;
 }
@@ -527,7 +545,10 @@ int ort_load_mesh(const char *path, float **vertices, uint32_t *vertex_count, ui
 {
     if(!path || !vertices || !vertex_count || !indices || !index_count) { ort_set_last_error_("null argument"); return ORT_ERR_ARG; }
     std::vector<ort_v3> v; std::vector<uint32_t> i; std::string err;
-    int rc = ort::load_mesh_file(path, &v, &i, &err);
+    int rc = ORT_OK;
+    try { rc = ort::load_mesh_file(path, &v, &i, &err); }
+    catch(const std::bad_alloc &) { ort_set_last_error_("out of host memory while loading the mesh"); return ORT_ERR_LIMIT; }
+    catch(const std::exception &e) { ort_set_last_error_((std::string("mesh loader: ") + e.what()).c_str()); return ORT_ERR_PARSE; }
     if(rc != ORT_OK) { ort_set_last_error_(err.c_str()); return rc; }
     *vertex_count = (uint32_t)v.size(); *index_count = (uint32_t)i.size();
     *vertices = (float *)malloc(sizeof(ort_v3) * (v.size() ? v.size() : 1));

@@ -46,7 +46,7 @@ int fail(int code, const std::string &msg)
 struct WfPool
 {
     WfBuffers wf;
-    uint32_t *d_sort;                       // EXTEND's chunk counter | SHADE's tile counter
+    uint32_t *d_sort;                       // hist[512] | cursor[512] | live | chunk counter
     unsigned int *d_active, *h_active;      // 2 x WF_BATCH "slots still active" counters
     cudaStream_t stream;
     cudaEvent_t done[2], ev[2][WF_BATCH][4];
@@ -64,7 +64,6 @@ struct OrtScene
     // device arrays (layout: bvh.h, scene_flatten.h)
     q4 *d_nodes, *d_prims, *d_cyl, *d_materials;
     uint8_t *d_light_is_sphere;
-    uint8_t *d_mat_class;               // per material: is_light << 3 | lobes -- the material's share of the shading class (wavefront.cuh)
     uint32_t node_count, prim_count, light_count;
     // scratch owned by the handle
     unsigned long long *d_stats;        // STAT_COUNT counters
@@ -75,7 +74,7 @@ struct OrtScene
     cudaEvent_t ev0, ev1;
     int sm_count;
     int mega_blocks_per_sm, mega_blocks_per_sm_count;
-    int wf_extend_blocks, wf_shade_blocks;
+    int wf_extend_blocks;
     uint32_t extend_launches;           // EXTEND launches of the last wavefront render
     uint32_t stack_rows;                // wide-tree depth + 1: rows of the shared-memory traversal stack
     float extend_ms, shade_ms, sort_ms; // summed stage times of the last wavefront render
@@ -83,7 +82,7 @@ struct OrtScene
     WfBuffers wf;                       // the whole allocation; pools[] view shares of it
     unsigned int *d_active;             // per-iteration "slots still active" counters
     unsigned int *h_active;             // pinned mirror
-    uint32_t *d_sort;                   // per pool: EXTEND's chunk counter | SHADE's tile counter
+    uint32_t *d_sort;                   // per pool: hist[512] | cursor[512] | live | chunk counter
     WfPool pools[WF_MAX_POOLS];
     int wf_ready;
     cudaEvent_t wf_start;
@@ -98,7 +97,6 @@ struct OrtScene
         SceneView v;
         v.nodes = d_nodes; v.prims = d_prims; v.cyl = d_cyl;
         v.node_count = node_count; v.prim_count = prim_count; v.main_root = main_root; v.tri_root = tri_root;
-        v.mat_class = d_mat_class;
         return v;
     }
 };
@@ -198,7 +196,7 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
 {
     if(!s->wf_ready)
     {
-        CUDA_TRY(cudaMalloc((void **)&s->d_sort, WF_MAX_POOLS * 2 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc((void **)&s->d_sort, WF_MAX_POOLS * (2 * WF_KEY_BINS + 2) * sizeof(uint32_t)));
         CUDA_TRY(cudaMalloc((void **)&s->d_active, WF_MAX_POOLS * 2 * WF_BATCH * sizeof(unsigned int)));
         CUDA_TRY(cudaMallocHost((void **)&s->h_active, WF_MAX_POOLS * 2 * WF_BATCH * sizeof(unsigned int)));
         CUDA_TRY(cudaEventCreateWithFlags(&s->wf_start, cudaEventDisableTiming));
@@ -212,17 +210,18 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
                 for(int it = 0; it < WF_BATCH; ++it)
                     for(int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreate(&pl.ev[b][it][k]));
             }
-            pl.d_sort = s->d_sort + p * 2;
+            pl.d_sort = s->d_sort + p * (2 * WF_KEY_BINS + 2);
             pl.d_active = s->d_active + p * 2 * WF_BATCH;
             pl.h_active = s->h_active + p * 2 * WF_BATCH;
         }
         s->wf_ready = 1;
     }
     if(s->wf.capacity >= capacity) return ORT_OK;
-    cudaFree(s->wf.rec); cudaFree(s->wf.key);
+    cudaFree(s->wf.rec); cudaFree(s->wf.key); cudaFree(s->wf.perm);
     memset(&s->wf, 0, sizeof(s->wf));
     CUDA_TRY(cudaMalloc((void **)&s->wf.rec, (size_t)capacity * WF_REC_QUADS * sizeof(float4)));
-    CUDA_TRY(cudaMalloc((void **)&s->wf.key, (size_t)capacity * sizeof(uint8_t)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.key, (size_t)capacity * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&s->wf.perm, (size_t)capacity * sizeof(uint32_t)));
     s->wf.capacity = capacity;
     return ORT_OK;
 }
@@ -244,20 +243,13 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     int rc = ensure_wavefront(s, capacity);
     if(rc != ORT_OK) return rc;
     const int sorted = getenv("ORT_WF_NOSORT") ? 0 : 1;
-    // EXTEND's dynamic shared memory: the rays' constants (WF_RAY_ROWS float4 per thread) + the traversal stacks
-    const size_t stack_bytes = (size_t)WF_RAY_ROWS * 128 * sizeof(float4) + (size_t)s->stack_rows * 128 * sizeof(uint2);
+    const size_t stack_bytes = (size_t)s->stack_rows * 128 * sizeof(uint2);
     // persistent EXTEND grid: as many 4-warp blocks as stay resident
     if(s->wf_extend_blocks == 0)
     {
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_extend<false>, 128, stack_bytes));
         s->wf_extend_blocks = (nb > 0 ? nb : 1) * s->sm_count;
-    }
-    if(s->wf_shade_blocks == 0)
-    {
-        int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wf_shade, 128, 0));
-        s->wf_shade_blocks = (nb > 0 ? nb : 1) * s->sm_count;
     }
     const int extend_blocks_per_sm = getenv("ORT_WF_EXTEND_BPSM") ? atoi(getenv("ORT_WF_EXTEND_BPSM")) : 0;
     s->extend_ms = s->shade_ms = s->sort_ms = 0.f;
@@ -275,6 +267,7 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         if(lo > hi) lo = hi;
         pl.wf.rec = s->wf.rec + (size_t)WF_REC_QUADS * lo;
         pl.wf.key = s->wf.key + lo;
+        pl.wf.perm = s->wf.perm + lo;
         pl.wf.capacity = hi - lo;
         pl.cur = 0; pl.finished = pl.wf.capacity == 0;
         CUDA_TRY(cudaStreamWaitEvent(pl.stream, s->wf_start, 0));
@@ -283,26 +276,34 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
     auto enqueue = [&](WfPool &pl, int b) -> int
     {
         const uint32_t cap = pl.wf.capacity;
+        const unsigned grid = (cap + 127u) / 128u;
         unsigned egrid = (unsigned)s->wf_extend_blocks;
         if(extend_blocks_per_sm > 0 && (unsigned)(extend_blocks_per_sm * s->sm_count) < egrid) egrid = (unsigned)(extend_blocks_per_sm * s->sm_count);
-        if(egrid > (cap + 127u) / 128u) egrid = (cap + 127u) / 128u;
-        unsigned sgrid = (unsigned)s->wf_shade_blocks;
-        if(sgrid > (cap + WF_TILE - 1u) / WF_TILE) sgrid = (cap + WF_TILE - 1u) / WF_TILE;
-        uint32_t *chunk_counter = pl.d_sort, *tile_counter = pl.d_sort + 1;
+        if(egrid > grid) egrid = grid;
+        uint32_t *hist = pl.d_sort, *cursor = pl.d_sort + WF_KEY_BINS, *live = pl.d_sort + 2 * WF_KEY_BINS;
+        uint32_t *chunk_counter = pl.d_sort + 2 * WF_KEY_BINS + 1;
         unsigned int *act = pl.d_active + b * WF_BATCH;
         cudaStream_t st = pl.stream;
         CUDA_TRY(cudaMemsetAsync(act, 0, WF_BATCH * sizeof(unsigned int), st));
         for(int it = 0; it < WF_BATCH; ++it)
         {
-            CUDA_TRY(cudaMemsetAsync(pl.d_sort, 0, 2 * sizeof(uint32_t), st));
+            CUDA_TRY(cudaMemsetAsync(hist, 0, WF_KEY_BINS * sizeof(uint32_t), st));
+            CUDA_TRY(cudaMemsetAsync(chunk_counter, 0, sizeof(uint32_t), st));
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][0], st));
 #ifdef ORT_COUNTERS
-            k_wf_extend<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats);
+            k_wf_extend<true><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
 #else
-            k_wf_extend<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats);
+            k_wf_extend<false><<<egrid, 128, stack_bytes, st>>>(a.scene, pl.wf, chunk_counter, a.stats, hist);
 #endif
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][1], st));
-            k_wf_shade<<<sgrid, 128, 0, st>>>(a, pl.wf, act + it, tile_counter, sorted);
+            if(sorted)
+            {
+                k_wf_scan<<<1, WF_KEY_BINS, 0, st>>>(hist, cursor, live);
+                k_wf_scatter<<<(cap + 1023u) / 1024u, 1024, 0, st>>>(pl.wf, cursor);
+                *launches += 2;
+            }
+            CUDA_TRY(cudaEventRecord(pl.ev[b][it][2], st));
+            k_wf_shade<<<grid, 128, 0, st>>>(a, pl.wf, act + it, live, sorted);
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][3], st));
         }
         *launches += 2 * WF_BATCH;
@@ -316,10 +317,11 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         CUDA_TRY(cudaEventSynchronize(pl.done[b]));
         for(int it = 0; it < WF_BATCH; ++it)
         {
-            float e = 0.f, sh = 0.f;
+            float e = 0.f, so = 0.f, sh = 0.f;
             cudaEventElapsedTime(&e, pl.ev[b][it][0], pl.ev[b][it][1]);
-            cudaEventElapsedTime(&sh, pl.ev[b][it][1], pl.ev[b][it][3]);
-            s->extend_ms += e; s->shade_ms += sh;       // the class sort now runs inside SHADE: sort_ms stays 0
+            cudaEventElapsedTime(&so, pl.ev[b][it][1], pl.ev[b][it][2]);
+            cudaEventElapsedTime(&sh, pl.ev[b][it][2], pl.ev[b][it][3]);
+            s->extend_ms += e; s->sort_ms += so; s->shade_ms += sh;
             s->extend_launches += 1;
         }
         *finished = pl.h_active[b * WF_BATCH + WF_BATCH - 1] == 0;
@@ -331,12 +333,9 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         WfPool &pl = s->pools[p];
         if(pl.finished) continue;
         const unsigned grid = (pl.wf.capacity + 127u) / 128u;
-        unsigned sgrid = (unsigned)s->wf_shade_blocks;
-        if(sgrid > (pl.wf.capacity + WF_TILE - 1u) / WF_TILE) sgrid = (pl.wf.capacity + WF_TILE - 1u) / WF_TILE;
         k_wf_reset<<<grid, 128, 0, pl.stream>>>(pl.wf);
         CUDA_TRY(cudaMemsetAsync(pl.d_active, 0, 2 * WF_BATCH * sizeof(unsigned int), pl.stream));
-        CUDA_TRY(cudaMemsetAsync(pl.d_sort, 0, 2 * sizeof(uint32_t), pl.stream));
-        k_wf_shade<<<sgrid, 128, 0, pl.stream>>>(a, pl.wf, pl.d_active, pl.d_sort + 1, sorted);
+        k_wf_shade<<<grid, 128, 0, pl.stream>>>(a, pl.wf, pl.d_active, pl.d_sort + 2 * WF_KEY_BINS, 0);
         *launches += 2;
         rc = enqueue(pl, 0);
         if(rc != ORT_OK) return rc;
@@ -622,12 +621,6 @@ static int make_scene_handle(FlatScene &flat, build::DeviceBuildResult &built, b
     if(rc == ORT_OK) rc = upload(&s->d_cyl, flat.cylinders.data(), flat.cylinders.size() * sizeof(CylinderAux), &total);
     if(rc == ORT_OK) rc = upload(&s->d_materials, flat.materials.data(), flat.materials.size() * sizeof(DevMaterial), &total);
     if(rc == ORT_OK) rc = upload(&s->d_light_is_sphere, flat.light_is_sphere.data(), flat.light_is_sphere.size(), &total);
-    if(rc == ORT_OK)
-    {
-        std::vector<uint8_t> cls(flat.materials.size());
-        for(size_t i = 0; i < cls.size(); ++i) cls[i] = (uint8_t)((flat.materials[i].is_light ? 8u : 0u) | (flat.materials[i].lobes & 7u));
-        rc = upload(&s->d_mat_class, cls.data(), cls.size(), &total);
-    }
     if(rc == ORT_OK) rc = upload(&s->d_stats, (const void *)0, 0, &total);
     if(rc != ORT_OK) { ort_scene_destroy(s); return rc; }
     cudaFree(s->d_stats); s->d_stats = 0;
@@ -655,6 +648,7 @@ static int check_device(int device, OrtScene **scene_out)
 
 int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_node, int device, uint32_t flags, OrtScene **scene_out)
 {
+    ORT_GUARD_BEGIN
     int rc = check_device(device, scene_out);
     if(rc != ORT_OK) return rc;
     FlatScene flat;
@@ -666,10 +660,12 @@ int ort_scene_create_ex(const OrtWorld *world, const OrtBVHOctreeNode *top_most_
     if(rc != ORT_OK) return fail(rc, err);
     bs.collect_s = (float)seconds_since(t0);
     return create_scene_from_records(prims, flat, device, flags, bs, scene_out);
+    ORT_GUARD_END
 }
 
 int ort_scene_create_from_lists(const OrtWorld *world, const OrtShapeLists *lists, int device, uint32_t flags, OrtScene **scene_out)
 {
+    ORT_GUARD_BEGIN
     int rc = check_device(device, scene_out);
     if(rc != ORT_OK) return rc;
     FlatScene flat;
@@ -722,6 +718,7 @@ int ort_scene_create_from_lists(const OrtWorld *world, const OrtShapeLists *list
     if(rc != ORT_OK) return fail(rc, err);
     bs.collect_s = (float)seconds_since(t0);
     return create_scene_from_records(prims, flat, device, flags, bs, scene_out);
+    ORT_GUARD_END
 }
 
 int ort_scene_build_stats(const OrtScene *s, OrtBuildStats *out)
@@ -770,7 +767,7 @@ int ort_scene_destroy(OrtScene *s)
             }
         }
     }
-    cudaFree(s->wf.key); cudaFree(s->d_sort); cudaFree(s->d_mat_class);
+    cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->d_sort);
     if(s->h_active) cudaFreeHost(s->h_active);
     if(s->ev0) cudaEventDestroy(s->ev0);
     if(s->ev1) cudaEventDestroy(s->ev1);
@@ -937,10 +934,12 @@ int ort_render_hdr(OrtScene *s, const OrtCamera *camera, const OrtRenderParams *
 {
     if(!path || !P) return fail(ORT_ERR_ARG, "null argument");
     if(P->output_width <= 0 || P->output_height <= 0) return fail(ORT_ERR_ARG, "bad image size");
+    ORT_GUARD_BEGIN
     std::vector<uint32_t> words((size_t)P->output_width * P->output_height);
     int rc = ort_render_rgbe(s, camera, P, words.data(), stats);
     if(rc != ORT_OK) return rc;
     return ort_write_hdr_rgbe(path, words.data(), P->output_width, P->output_height);
+    ORT_GUARD_END
 }
 
 int ort_tiled_raytrace_bvh(OrtScene *scene, const OrtCamera *camera, ort_v3 *output_buffer,

@@ -142,6 +142,58 @@ __global__ void k_gen_random_rays(f3 lo, f3 hi, uint32_t seed, unsigned long lon
     dirs[3 * i] = d.x; dirs[3 * i + 1] = d.y; dirs[3 * i + 2] = d.z;
 }
 
+
+// ---- mesh bake (code/macos_main.mm:382-413) ----------------------------------------------
+// v *= scale; v = quaternion_rotation(q, quaternion_rotation((0,1,0), degree, v)); v += translate -- the IEEE
+// operations of code/math.h:746-795 in their order, no contraction, so the baked vertices have the bits the
+// reference's (and this library's host) bake produces.  The axis quaternion (cosf / sinf of the half angle) is
+// a per-mesh constant and is formed on the host, like every libm value that reaches the geometry.
+__device__ __forceinline__ f3 quat_rotate_dev(float4 q, f3 v)          // math.h:774-795 (q = x, y, z, w)
+{
+    float m00 = 1.0f - 2 * q.y * q.y - 2 * q.z * q.z;
+    float m01 = 2 * q.x * q.y - 2 * q.w * q.z;
+    float m02 = 2 * q.x * q.z + 2 * q.w * q.y;
+    float m10 = 2 * q.x * q.y + 2 * q.w * q.z;
+    float m11 = 1.0f - 2 * q.x * q.x - 2 * q.z * q.z;
+    float m12 = 2 * q.y * q.z - 2 * q.w * q.x;
+    float m20 = 2 * q.x * q.z - 2 * q.w * q.y;
+    float m21 = 2 * q.y * q.z + 2 * q.w * q.x;
+    float m22 = 1 - 2 * q.x * q.x - 2 * q.y * q.y;
+    return mk3(m00 * v.x + m01 * v.y + m02 * v.z, m10 * v.x + m11 * v.y + m12 * v.z, m20 * v.x + m21 * v.y + m22 * v.z);
+}
+// order-preserving map float -> uint32 for atomicMin / atomicMax
+__device__ __forceinline__ uint32_t f_ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float f_unord(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+
+// pass 1: bake + value bounds (ord[0..2] = min, ord[3..5] = max, as ordered integers)
+__global__ void k_bake_mesh(uint32_t n, const float *__restrict__ in, float *__restrict__ out, float scale, float4 q_axis, float4 q,
+                            f3 translate, uint32_t *__restrict__ ord)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    f3 v = mk3(in[3 * i] * scale, in[3 * i + 1] * scale, in[3 * i + 2] * scale);
+    v = quat_rotate_dev(q, quat_rotate_dev(q_axis, v));
+    v = v + translate;
+    out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+    atomicMin(&ord[0], f_ord(v.x)); atomicMin(&ord[1], f_ord(v.y)); atomicMin(&ord[2], f_ord(v.z));
+    atomicMax(&ord[3], f_ord(v.x)); atomicMax(&ord[4], f_ord(v.y)); atomicMax(&ord[5], f_ord(v.z));
+}
+// pass 2: the reference folds the vertices sequentially with `(a < b) ? a : b` (types.h:50-51), which keeps the
+// LATER of two equal values -- visible only when the bound is a zero whose sign differs between vertices.
+// last[k] = highest vertex index whose component EQUALS the bound (IEEE ==, so +0 == -0).
+__global__ void k_bake_last(uint32_t n, const float *__restrict__ out, const uint32_t *__restrict__ ord, uint32_t *__restrict__ last)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+    {
+        float v = out[3 * i + k];
+        if(v == f_unord(ord[k])) atomicMax(&last[k], i + 1u);
+        if(v == f_unord(ord[3 + k])) atomicMax(&last[3 + k], i + 1u);
+    }
+}
+
 struct DevBuf
 {
     void *p = 0;
@@ -275,6 +327,48 @@ int ort_selftest_bsdf(int device, uint32_t n, const float *mat10, const float *N
     ORT_CUDA_TRY(cudaMemcpy(state_after, o_st.p, s1, cudaMemcpyDeviceToHost));
     ORT_CUDA_TRY(cudaMemcpy(pdf, o_pdf.p, s1, cudaMemcpyDeviceToHost));
     ORT_CUDA_TRY(cudaMemcpy(eval, o_ev.p, v3, cudaMemcpyDeviceToHost));
+    return ORT_OK;
+    ORT_GUARD_END
+}
+
+
+int ort_bake_mesh(int device, uint32_t vertex_count, const ort_v3 *vertices_in, ort_v3 *vertices_out,
+                  float scale, float degree, ort_v4 quaternion, ort_v3 translate, ort_v3 *aabb_min, ort_v3 *aabb_max)
+{
+    ORT_GUARD_BEGIN
+    if(vertex_count && (!vertices_in || !vertices_out)) return fail_with(ORT_ERR_ARG, "null argument");
+    if(!aabb_min || !aabb_max) return fail_with(ORT_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if(rc != ORT_OK) return rc;
+    // the empty fold: (FLT_MAX, FLT_MIN) -- FLT_MIN being the smallest POSITIVE float (macos_main.mm:383)
+    aabb_min->x = aabb_min->y = aabb_min->z = FLT_MAX;
+    aabb_max->x = aabb_max->y = aabb_max->z = FLT_MIN;
+    if(vertex_count == 0) return ORT_OK;
+    // quaternion_rotation(v3 axis = (0,1,0), rad, v), math.h:746-772: the quaternion of the axis rotation, on the host
+    const float rad = 0.0174533f * degree;
+    float4 qa; qa.w = cosf(rad / 2); qa.x = 0.0f * sinf(rad / 2); qa.y = 1.0f * sinf(rad / 2); qa.z = 0.0f * sinf(rad / 2);
+    float4 q; q.x = quaternion.x; q.y = quaternion.y; q.z = quaternion.z; q.w = quaternion.w;
+    DevBuf d_in, d_out, d_ord, d_last;
+    const size_t bytes = (size_t)vertex_count * 3 * sizeof(float);
+    ORT_CUDA_TRY(d_in.alloc(bytes)); ORT_CUDA_TRY(d_out.alloc(bytes)); ORT_CUDA_TRY(d_ord.alloc(6 * 4)); ORT_CUDA_TRY(d_last.alloc(6 * 4));
+    uint32_t init[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+    ORT_CUDA_TRY(cudaMemcpy(d_in.p, vertices_in, bytes, cudaMemcpyHostToDevice));
+    ORT_CUDA_TRY(cudaMemcpy(d_ord.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    ORT_CUDA_TRY(cudaMemset(d_last.p, 0, 6 * 4));
+    const unsigned grid = (vertex_count + 255u) / 256u;
+    k_bake_mesh<<<grid, 256>>>(vertex_count, d_in.as<float>(), d_out.as<float>(), scale, qa, q, mk3(translate.x, translate.y, translate.z), d_ord.as<uint32_t>());
+    k_bake_last<<<grid, 256>>>(vertex_count, d_out.as<float>(), d_ord.as<uint32_t>(), d_last.as<uint32_t>());
+    ORT_CUDA_TRY(cudaGetLastError());
+    ORT_CUDA_TRY(cudaMemcpy(vertices_out, d_out.p, bytes, cudaMemcpyDeviceToHost));
+    uint32_t last[6];
+    ORT_CUDA_TRY(cudaMemcpy(last, d_last.p, sizeof(last), cudaMemcpyDeviceToHost));
+    float *mn = &aabb_min->x, *mx = &aabb_max->x;
+    for(int k = 0; k < 3; ++k)
+    {
+        // every vertex is finite here or the bound has no last index: then the fold's start value stands
+        if(last[k]) { float v = (&vertices_out[last[k] - 1u].x)[k]; if(!(FLT_MAX < v)) mn[k] = v; }
+        if(last[3 + k]) { float v = (&vertices_out[last[3 + k] - 1u].x)[k]; if(!(FLT_MIN > v)) mx[k] = v; }
+    }
     return ORT_OK;
     ORT_GUARD_END
 }

@@ -92,6 +92,15 @@ void prim_bounds(HostPrim &p)
     }
 }
 
+// a record whose bounds are not finite (NaN / Inf vertices or parameters) cannot be placed in any tree: the
+// builders would loop on an infinite extent or cast NaN to an integer.  Rejected with ORT_ERR_ARG instead.
+bool prim_is_finite(const HostPrim &p)
+{
+    for(int k = 0; k < 3; ++k)
+        if(!(p.lo[k] >= -1e30f && p.lo[k] <= 1e30f && p.hi[k] >= -1e30f && p.hi[k] <= 1e30f)) return false;
+    return true;
+}
+
 } // namespace
 
 // the per-material constants of DevMaterial, exactly as path.h's pdf_brdf / sample_brdf /
@@ -208,6 +217,8 @@ int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
                 {
                     OrtTriangle s; memcpy(&s, q, sizeof(s));
                     if(!s.mesh || !s.mesh->vertices) { *err = "triangle record without mesh"; return ORT_ERR_ARG; }
+                    if(s.i_0 >= s.mesh->vertex_count || s.i_1 >= s.mesh->vertex_count || s.i_2 >= s.mesh->vertex_count)
+                    { *err = "triangle record with vertex index out of range"; return ORT_ERR_ARG; }
                     p.kind = PRIM_TRIANGLE;
                     p.a = v3(s.mesh->vertices[s.i_0]);       // ray.cpp:702-704
                     p.b = v3(s.mesh->vertices[s.i_1]);
@@ -227,6 +238,7 @@ int collect_records(const OrtWorld *world, const OrtBVHOctreeNode *root,
             {
                 if(p.mat >= world->mat_count) { *err = "record with material index out of range"; return ORT_ERR_ARG; }
                 prim_bounds(p);
+                if(!prim_is_finite(p)) { *err = "record with non-finite geometry (NaN / Inf)"; return ORT_ERR_ARG; }
                 prims->push_back(p);
             }
         }
@@ -875,6 +887,7 @@ int collect_records_from_lists(const OrtWorld *world, const OrtShapeLists *L,
         else { out->info.csg_count++; continue; }       // inert record, ray.cpp:718-767: a rank, nothing to test
         if(p.mat >= world->mat_count) { *err = "record with material index out of range"; return ORT_ERR_ARG; }
         prim_bounds(p);
+        if(!prim_is_finite(p)) { *err = "record with non-finite geometry (NaN / Inf)"; return ORT_ERR_ARG; }
         prims->push_back(p);
     }
     out->info.record_count = (uint32_t)n;
@@ -1027,6 +1040,7 @@ int collect_analytic(const OrtWorld *world, const OrtShapeLists *L, f3 root_cent
     {
         if((*analytic)[i].mat >= world->mat_count) { *err = "record with material index out of range"; return ORT_ERR_ARG; }
         prim_bounds((*analytic)[i]);
+        if(!prim_is_finite((*analytic)[i])) { *err = "record with non-finite geometry (NaN / Inf)"; return ORT_ERR_ARG; }
     }
     return ORT_OK;
 }

@@ -115,3 +115,65 @@ def test_scene_from_shape_lists_on_the_device(ort, scene):
     ib_, _ = b.render(hs2.camera, P)
     assert np.array_equal(bits(ia_), bits(ib_))
     a.close(); b.close()
+
+
+def test_mesh_bake_on_the_device_is_bit_identical(ort, data_dir):
+    """the mesh bake (scale -> rotate about (0,1,0) -> quaternion -> translate + the AABB fold that
+    starts at (FLT_MAX, FLT_MIN), code/macos_main.mm:382-413) as a CUDA kernel: vertices and boxes of every mesh of
+    the BASELINE scenes equal the host bake bit for bit (PLY + OBJ, with and without the extra z rotation)"""
+    for name in ("c3_bunny_box", "c4_dwarf_hdr"):
+        scn = os.path.join(ol.SCENES_DIR, name + ".scn")
+        a = ort.HostScene.load(scn, data_dir, 64, 36)
+        b = ort.HostScene.load(scn, data_dir, 64, 36, bake_on_device=True)
+        ma, mb = a.meshes(), b.meshes()
+        assert len(ma) == len(mb) >= 1
+        for (va, ia, mna, mxa, mata), (vb, ib, mnb, mxb, matb) in zip(ma, mb):
+            assert np.array_equal(va.view(np.uint32), vb.view(np.uint32))
+            assert np.array_equal(ia, ib) and mata == matb
+            assert np.array_equal(mna.view(np.uint32), mnb.view(np.uint32)) and np.array_equal(mxa.view(np.uint32), mxb.view(np.uint32))
+        # and the scenes built from them are the same scene
+        sa, sb = ort.Scene(a.world, a.root, 0), ort.Scene(b.world, b.root, 0)
+        na, pa = sa.download(); nb, pb = sb.download()
+        assert np.array_equal(na, nb) and np.array_equal(pa, pb)
+        sa.close(); sb.close(); a.close(); b.close()
+
+
+def test_mesh_bake_box_quirks_on_the_device(ort):
+    """the fold starts at FLT_MIN = smallest POSITIVE float, so a mesh in negative space keeps max = 1.18e-38
+    (ray.cpp:1761, macos_main.mm:383); among equal values the later vertex wins ((a < b) ? a : b, types.h:50-51),
+    which decides the sign of a zero bound; an empty mesh returns the start values"""
+    flt_min = np.float32(1.17549435e-38)
+    v = np.array([[-1.0, -2.0, -3.0], [-0.5, -0.25, -4.0], [-2.0, -1.0, -0.125]], np.float32)
+    out, mn, mx = ort.bake_mesh(v, 1.0, 0.0, (0, 0, 0, 1), (0, 0, 0))
+    assert np.array_equal(out, v)
+    assert np.array_equal(mn, np.array([-2.0, -2.0, -4.0], np.float32)) and np.all(mx == flt_min)
+    z = np.array([[0.0, 1.0, 2.0], [-0.0, 1.0, 2.0], [3.0, 1.0, 2.0]], np.float32)
+    _, mn, _ = ort.bake_mesh(z, 1.0, 0.0, (0, 0, 0, 1), (0, 0, 0))
+    assert mn.view(np.uint32)[0] == 0x80000000          # -0 came later than +0
+    _, mn, _ = ort.bake_mesh(z[[1, 0, 2]], 1.0, 0.0, (0, 0, 0, 1), (0, 0, 0))
+    assert mn.view(np.uint32)[0] == 0x00000000          # +0 came later
+    _, mn, mx = ort.bake_mesh(np.zeros((0, 3), np.float32), 2.0, 30.0, (0, 0, 0.707107, 0.707106), (1, 2, 3))
+    assert np.all(mn == np.finfo(np.float32).max) and np.all(mx == flt_min)
+
+
+def test_non_finite_geometry_is_rejected(ort, tmp_path):
+    """NaN / Inf vertices cannot be placed in any tree: ort_scene_create* reports ORT_ERR_ARG on every path
+    (octree hand-off, shape lists on the host, shape lists on the device) instead of building a wrong tree"""
+    for bad in ("nan", "inf"):
+        ply = tmp_path / ("bad_%s.ply" % bad)
+        ply.write_text("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+                       "element face 2\nproperty list uchar int vertex_indices\nend_header\n"
+                       "0.0 0.0 0.0\n1.0 0.0 0.0\n0.0 1.0 0.0\n1.0 1.0 0.5\n3 0 1 2\n3 1 3 2\n")
+        scn = tmp_path / ("bad_%s.scn" % bad)
+        scn.write_text("camera 0.0 0.0 5.0 b 0.2 q 1.0 0.0 0.0 0.0\nbrdf 0.5 0.5 0.5 0.0 0.0 0.0 10\n"
+                       "mesh bad_%s.ply 0.0 0.0 0.0 1.0 q 1.0 0.0 0.0 0.0\n" % bad)
+        hs = ort.HostScene.load(str(scn), str(tmp_path), 32, 18, octree=False)
+        # poison one baked vertex in place (the structs are the data contract: host pointers)
+        import ctypes as C2
+        n = C2.c_uint32(0)
+        m = C2.cast(ort.lib().ort_host_scene_meshes(hs.h, C2.byref(n)), C2.POINTER(ort.api.Mesh))[0]
+        C2.cast(m.vertices, C2.POINTER(C2.c_float))[4] = float(bad)
+        for on_device in (False, True):
+            with pytest.raises(ort.OrtError, match="non-finite"):
+                ort.Scene.from_lists(hs.world, hs.lists(), 0, build_on_device=on_device)
+        hs.close()

@@ -111,6 +111,22 @@ def test_loader_errors_are_reported_not_fatal(ort, tmp_path):
         ort.HostScene.load(str(nomesh), str(tmp_path) + "/", 32, 32)
     with pytest.raises(ort.OrtError):
         ort.load_mesh(str(tmp_path / "x.stl"))
+    # hostile counts are parse errors, not allocations: a face arity / vertex count the file cannot hold,
+    # and a face line that runs out of indices
+    hdr = ("ply\nformat ascii 1.0\nelement vertex %s\nproperty float x\nproperty float y\nproperty float z\n"
+           "element face 1\nproperty list uchar int vertex_indices\nend_header\n")
+    f = tmp_path / "arity.ply"
+    f.write_text(hdr % "3" + "0 0 0\n1 0 0\n0 1 0\n2000000000 0 1 2\n")
+    with pytest.raises(ort.OrtError, match="arity"):
+        ort.load_mesh(str(f))
+    f = tmp_path / "count.ply"
+    f.write_text(hdr % "2000000000" + "0 0 0\n")
+    with pytest.raises(ort.OrtError, match="vertex count"):
+        ort.load_mesh(str(f))
+    f = tmp_path / "short.ply"
+    f.write_text(hdr % "3" + "0 0 0\n1 0 0\n0 1 0\n4 0 1 2 1.5\n")
+    with pytest.raises(ort.OrtError, match="malformed face"):
+        ort.load_mesh(str(f))
 
 
 def test_ragged_and_empty_meshes(ort, tmp_path):
