@@ -149,7 +149,8 @@ def lib(path=None):
     L.ort_raycast_brute_device.argtypes = [vp, c_u64, vp, vp, vp, vp, vp, vp]
     L.ort_raycast_counters_device.argtypes = [vp, c_u64, vp, vp, C.POINTER(c_u64), C.POINTER(c_u64), C.POINTER(c_u64)]
     L.ort_scene_device.argtypes = [vp, C.POINTER(C.c_int)]
-    L.ort_bake_mesh.argtypes = [C.c_int, c_u32, vp, vp, c_f, c_f, V4, V3, C.POINTER(V3), C.POINTER(V3)]
+    if hasattr(L, "ort_bake_mesh"):
+        L.ort_bake_mesh.argtypes = [C.c_int, c_u32, vp, vp, c_f, c_f, V4, V3, C.POINTER(V3), C.POINTER(V3)]
     L.ort_measure_l2_bandwidth.argtypes = [C.c_int, c_u32, C.POINTER(c_f)]
     L.ort_selftest_intersect.argtypes = [C.c_int, c_u32, c_u32, vp, vp]
     L.ort_selftest_bsdf.argtypes = [C.c_int, c_u32, vp, vp, vp, vp, vp, vp, c_f, vp, vp, vp, vp, vp]

@@ -163,13 +163,17 @@ ORT_HD float byte_f_xu(uint32_t w, uint32_t k) { return (float)((w >> (8u * k)) 
 #define ORT_I2F_PLANES 5
 #endif
 
-// packed f32x2 FMA for the slab test (sm_100: fma.rn.f32x2); the host build keeps the scalar form
+// Packed f32x2 FMA for the slab test (sm_100: fma.rn.f32x2, __ffma2_rn) -- built, bit-identical, measured on
+// B200 and left OFF: 24 FFMA2 instead of 48 FFMA per node visit (SASS: 1344 -> 1264 instructions), yet EXTEND
+// is ~1 % SLOWER (C3 1080p x 64 spp 90.3 vs 89.2 ms, C4 83.9 vs 82.8, 4.4 M-triangle grid 115.3 vs 113.9): the
+// FMA pipe was never the busy one (ncu: fma 25 %, alu 58 %, xu 52 %) and the register pairs the packed form
+// needs cost more than the saved issue slots.  -DORT_SLAB_FMA2=1 selects it (device only).
 #ifndef ORT_SLAB_FMA2
-#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
-#define ORT_SLAB_FMA2 1
-#else
 #define ORT_SLAB_FMA2 0
 #endif
+#if ORT_SLAB_FMA2 && !(defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000))
+#undef ORT_SLAB_FMA2
+#define ORT_SLAB_FMA2 0
 #endif
 
 // traversal stack of pending node groups: a per-thread array here; the wavefront extend

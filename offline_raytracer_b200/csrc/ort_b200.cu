@@ -217,9 +217,12 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
         s->wf_ready = 1;
     }
     if(s->wf.capacity >= capacity) return ORT_OK;
-    cudaFree(s->wf.rec); cudaFree(s->wf.key); cudaFree(s->wf.perm);
+    cudaFree(s->wf.rec); cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->wf.cold);
     memset(&s->wf, 0, sizeof(s->wf));
     CUDA_TRY(cudaMalloc((void **)&s->wf.rec, (size_t)capacity * WF_REC_QUADS * sizeof(float4)));
+#if WF_SPLIT_COLD
+    CUDA_TRY(cudaMalloc((void **)&s->wf.cold, (size_t)capacity * 2 * sizeof(float4)));
+#endif
     CUDA_TRY(cudaMalloc((void **)&s->wf.key, (size_t)capacity * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.perm, (size_t)capacity * sizeof(uint32_t)));
     s->wf.capacity = capacity;
@@ -266,6 +269,7 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         if(hi > capacity || p == n_pools - 1) hi = capacity;
         if(lo > hi) lo = hi;
         pl.wf.rec = s->wf.rec + (size_t)WF_REC_QUADS * lo;
+        pl.wf.cold = s->wf.cold ? s->wf.cold + 2ull * lo : 0;
         pl.wf.key = s->wf.key + lo;
         pl.wf.perm = s->wf.perm + lo;
         pl.wf.capacity = hi - lo;
@@ -767,7 +771,7 @@ int ort_scene_destroy(OrtScene *s)
             }
         }
     }
-    cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->d_sort);
+    cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->wf.cold); cudaFree(s->d_sort);
     if(s->h_active) cudaFreeHost(s->h_active);
     if(s->ev0) cudaEventDestroy(s->ev0);
     if(s->ev1) cudaEventDestroy(s->ev1);

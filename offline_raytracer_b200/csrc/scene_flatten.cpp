@@ -96,8 +96,16 @@ void prim_bounds(HostPrim &p)
 // builders would loop on an infinite extent or cast NaN to an integer.  Rejected with ORT_ERR_ARG instead.
 bool prim_is_finite(const HostPrim &p)
 {
+    auto ok = [](float v) { return v >= -1e30f && v <= 1e30f; };          // false for NaN and +-Inf
+    auto ok3 = [&](f3 v) { return ok(v.x) && ok(v.y) && ok(v.z); };
+    // the parameters themselves (min / max folds drop NaNs, so the bounds alone would not show them) ...
+    if(!ok3(p.a)) return false;
+    if((p.kind == PRIM_TRIANGLE || p.kind == PRIM_AAB || p.kind == PRIM_CYLINDER) && !ok3(p.b)) return false;
+    if(p.kind == PRIM_TRIANGLE && !ok3(p.c)) return false;
+    if((p.kind == PRIM_SPHERE || p.kind == PRIM_CYLINDER) && !ok(p.radius)) return false;
+    // ... and the bounds derived from them
     for(int k = 0; k < 3; ++k)
-        if(!(p.lo[k] >= -1e30f && p.lo[k] <= 1e30f && p.hi[k] >= -1e30f && p.hi[k] <= 1e30f)) return false;
+        if(!ok(p.lo[k]) || !ok(p.hi[k])) return false;
     return true;
 }
 

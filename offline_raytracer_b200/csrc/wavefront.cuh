@@ -45,15 +45,37 @@ enum { WF_DEAD = 0u, WF_ACTIVE = 1u, WF_FRESH = 2u };
 __device__ __forceinline__ uint32_t wf_flags(uint32_t state, bool primary) { return (state << 29) | (primary ? 0x80000000u : 0u); }
 __device__ __forceinline__ uint32_t wf_state_of(uint32_t word) { return (word >> 29) & 3u; }
 
-#define WF_REC_QUADS 6u
+// WF_SPLIT_COLD: the two quads only ending paths touch (q4, q5) live in an array of their own, so that the
+// four hot quads are one 64-byte-aligned block -- exactly one L2 <- DRAM fetch at the default 64-byte
+// fetch granularity (measured variants: profiles/README.md)
+#ifndef WF_SPLIT_COLD
+#define WF_SPLIT_COLD 1
+#endif
+#ifndef WF_REC_QUADS
+#if WF_SPLIT_COLD
+#define WF_REC_QUADS 4u
+#else
+#define WF_REC_QUADS 6u       // 8u pads the record to 128 bytes
+#endif
+#endif
 
 struct WfBuffers
 {
     float4 *rec;         // WF_REC_QUADS quads per slot
+    float4 *cold;        // WF_SPLIT_COLD: q4, q5 of every slot (2 quads per slot); else unused
     uint32_t *key;       // shading key written by EXTEND: primary << 8 | min(material, 254); 511 = dead (so 256 | 255 must never be a live key)
     uint32_t *perm;      // slots grouped by key (counting sort)
     uint32_t capacity;
 };
+
+__device__ __forceinline__ float4 *wf_cold(const WfBuffers &wf, uint32_t slot)
+{
+#if WF_SPLIT_COLD
+    return wf.cold + 2ull * slot;
+#else
+    return wf.rec + (size_t)WF_REC_QUADS * slot + 4u;
+#endif
+}
 
 __global__ void k_wf_reset(WfBuffers wf)
 {
@@ -63,8 +85,9 @@ __global__ void k_wf_reset(WfBuffers wf)
         float4 *rec = wf.rec + (size_t)WF_REC_QUADS * i;
         rec[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(wf_flags(WF_FRESH, false)));
         rec[3] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_PIXEL_MASK | wf_flags(WF_FRESH, false)));
-        rec[4] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-        rec[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 *cold = wf_cold(wf, i);
+        cold[0] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        cold[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -110,10 +133,15 @@ __device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot,
 #endif
 // dynamic shared memory: (wide-tree depth + 1) stack rows of 128 uint2 -- sized per scene, so a
 // shallow tree does not pay for ORT_STACK_SIZE rows of occupancy
+#ifndef ORT_EXTEND_FULL_STORE
+#define ORT_EXTEND_FULL_STORE 0
+#endif
 #ifndef ORT_FETCH_MIN
 #define ORT_FETCH_MIN 8      // refill when at least this many lanes are idle (or none has a ray)
 #endif
-#define WF_CHUNK 256u        // slots a warp takes from the global counter at a time
+#ifndef WF_CHUNK
+#define WF_CHUNK 128u        // slots a warp takes from the global counter at a time (measured on B200: 64 / 128 / 256 / 512, profiles/README.md)
+#endif
 // one primitive test per trip instead of all the records a visit yielded (measured on B200, EXTEND ms:
 // C3 170.0 -> 167.9, testscene 71.3 -> 70.5, 4.4 M-triangle grid 229.6 -> 208.7)
 #ifndef ORT_EXTEND_ONE_PRIM
@@ -224,7 +252,13 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
             {
                 uint32_t mat = 0u;
                 if(t.best_prim != 0xFFFFFFFFu) mat = f2u(ldq(scene.prims + 3u * t.best_prim + 1u).w);
+#if ORT_EXTEND_FULL_STORE
+                // the whole sector (origin | t, direction | primitive) as two 128-bit stores instead of two 32-bit ones
+                wf.rec[WF_REC_QUADS * slot] = make_float4(t.o.x, t.o.y, t.o.z, t.best_t);
+                wf.rec[WF_REC_QUADS * slot + 1u] = make_float4(t.d.x, t.d.y, t.d.z, __uint_as_float(t.best_prim));
+#else
                 wf_store_hit(wf, slot, t.best_t, t.best_prim, mat);
+#endif
                 uint32_t key = (is_primary ? 256u : 0u) | (mat < 254u ? mat : 254u);
                 wf.key[slot] = key;
                 atomicAdd(&sh_hist[key], 1u);
@@ -427,7 +461,8 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
     {
         rg = sh_regen[threadIdx.x];
         float4 *rec = wf.rec + (size_t)WF_REC_QUADS * rg.slot;
-        float4 scol = rec[4], sch = rec[5];                 // the third sector: only paths that end touch it
+        float4 *cold = wf_cold(wf, rg.slot);
+        float4 scol = cold[0], sch = cold[1];               // the third sector: only paths that end touch it
         f3 color = mk3(scol.x, scol.y, scol.z) + mk3(rg.dx, rg.dy, rg.dz);
         uint32_t samples_left = __float_as_uint(scol.w), pixel_index = rg.pixel_index, chunk = __float_as_uint(sch.x);
         Path p;
@@ -497,8 +532,8 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
             rec[1] = make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(wf_flags(WF_ACTIVE, true)));
             rec[2] = make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series));
             rec[3] = make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index | wf_flags(WF_ACTIVE, true)));
-            rec[4] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left));
-            rec[5] = make_float4(__uint_as_float(chunk), 0.f, 0.f, 0.f);
+            cold[0] = make_float4(color.x, color.y, color.z, __uint_as_float(samples_left));
+            cold[1] = make_float4(__uint_as_float(chunk), 0.f, 0.f, 0.f);
             still_active += 1;
         }
     }

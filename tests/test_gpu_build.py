@@ -147,10 +147,13 @@ def test_mesh_bake_box_quirks_on_the_device(ort):
     out, mn, mx = ort.bake_mesh(v, 1.0, 0.0, (0, 0, 0, 1), (0, 0, 0))
     assert np.array_equal(out, v)
     assert np.array_equal(mn, np.array([-2.0, -2.0, -4.0], np.float32)) and np.all(mx == flt_min)
-    z = np.array([[0.0, 1.0, 2.0], [-0.0, 1.0, 2.0], [3.0, 1.0, 2.0]], np.float32)
-    _, mn, _ = ort.bake_mesh(z, 1.0, 0.0, (0, 0, 0, 1), (0, 0, 0))
+    # a baked coordinate of -0 needs every term of the rotation row and the translation to be a negative zero:
+    # x = 1*(-0) + 0*(-1) + 0*(-2) + (-0) = -0, while x = 1*(+0) + ... = +0
+    z = np.array([[0.0, -1.0, -2.0], [-0.0, -1.0, -2.0], [3.0, -1.0, -2.0]], np.float32)
+    out, mn, _ = ort.bake_mesh(z, 1.0, 0.0, (0, 0, 0, 1), (-0.0, 0, 0))
+    assert list(out[:, 0].view(np.uint32)) == [0x00000000, 0x80000000, 0x40400000]
     assert mn.view(np.uint32)[0] == 0x80000000          # -0 came later than +0
-    _, mn, _ = ort.bake_mesh(z[[1, 0, 2]], 1.0, 0.0, (0, 0, 0, 1), (0, 0, 0))
+    _, mn, _ = ort.bake_mesh(z[[1, 0, 2]], 1.0, 0.0, (0, 0, 0, 1), (-0.0, 0, 0))
     assert mn.view(np.uint32)[0] == 0x00000000          # +0 came later
     _, mn, mx = ort.bake_mesh(np.zeros((0, 3), np.float32), 2.0, 30.0, (0, 0, 0.707107, 0.707106), (1, 2, 3))
     assert np.all(mn == np.finfo(np.float32).max) and np.all(mx == flt_min)
