@@ -307,8 +307,9 @@ ORT_HD void trav_visit(const SceneView &s, T &t, Stack &st, float clip_t, TraceC
         // XORed with octinv so that the highest hit bit is the nearest child
         uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
         uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
-        uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-        uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        // per byte m: bits 5-7 = what to set (unary primitive count, or 1 for an inner child), bits 0-4 = where;
+        // a child's contribution to the hit mask is (m >> 5) << (m & 31) -- the shifter wraps at 32 on its own
+        uint32_t mx4 = meta4 ^ (octinv4 & inner_mask4 & 0x07070707u);
 #if ORT_SLAB_FMA2
 #pragma unroll
         for(uint32_t k = 0; k < 4; k += 2)
@@ -328,10 +329,9 @@ ORT_HD void trav_visit(const SceneView &s, T &t, Stack &st, float clip_t, TraceC
             float tmin0 = fmaxf(fmaxf(n0.x, n0.y), fmaxf(nz2.x, 0.0f)), tmax0 = fminf(fminf(f0.x, f0.y), fminf(fz2.x, t_clip));
             float tmin1 = fmaxf(fmaxf(n1_.x, n1_.y), fmaxf(nz2.y, 0.0f)), tmax1 = fminf(fminf(f1.x, f1.y), fminf(fz2.y, t_clip));
             if(COUNT == 1) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; if((meta4 >> (8u * (k + 1u))) & 0xFFu) cnt->box_tests++; }
-            uint32_t cb0 = (child_bits4 >> (8u * k)) & 0xFFu, bi0 = (bit_index4 >> (8u * k)) & 0xFFu;
-            uint32_t cb1 = (child_bits4 >> (8u * (k + 1u))) & 0xFFu, bi1 = (bit_index4 >> (8u * (k + 1u))) & 0xFFu;
-            hitmask |= (tmin0 <= tmax0) ? (cb0 << bi0) : 0u;
-            hitmask |= (tmin1 <= tmax1) ? (cb1 << bi1) : 0u;
+            uint32_t m0 = (mx4 >> (8u * k)) & 0xFFu, m1 = (mx4 >> (8u * (k + 1u))) & 0xFFu;
+            hitmask |= (tmin0 <= tmax0) ? ((m0 >> 5) << (m0 & 31u)) : 0u;
+            hitmask |= (tmin1 <= tmax1) ? ((m1 >> 5) << (m1 & 31u)) : 0u;
         }
 #else
 #pragma unroll
@@ -346,9 +346,8 @@ ORT_HD void trav_visit(const SceneView &s, T &t, Stack &st, float clip_t, TraceC
             float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
             float tmax = fminf(fminf(t1x, t1y), fminf(t1z, t_clip));
             if(COUNT == 1) { if((meta4 >> (8u * k)) & 0xFFu) cnt->box_tests++; }
-            uint32_t child_bits = (child_bits4 >> (8u * k)) & 0xFFu;
-            uint32_t bit_index = (bit_index4 >> (8u * k)) & 0xFFu;
-            hitmask |= (tmin <= tmax) ? (child_bits << bit_index) : 0u;
+            uint32_t m = (mx4 >> (8u * k)) & 0xFFu;
+            hitmask |= (tmin <= tmax) ? ((m >> 5) << (m & 31u)) : 0u;
         }
 #endif
     }

@@ -42,7 +42,30 @@ cap() {  # name, skip, args...
     gzip -f $OUT/${name}_extend_source.csv $OUT/${name}_shade_source.csv
     ls -la $OUT/${name}_full.ncu-rep
 }
+cap c3 120 --scene scenes/c3_bunny_box.scn --width 1920 --height 1080 --spp 64 --kernel 2 --reps 1
 cap c4 120 --scene scenes/c4_dwarf_hdr.scn --width 3840 --height 2160 --spp 32 --kernel 2 --reps 1
 cap c5lite 120 --scene scenes/c5_bunny_grid_64.scn --width 1920 --height 1080 --spp 32 --kernel 2 --reps 1
 cap c5 120 --scene scenes/c5_bunny_grid_729.scn --lists --width 3840 --height 2160 --spp 16 --kernel 2 --reps 1
-rm -f $OUT/c5lite_full.ncu-rep $OUT/c5_full.ncu-rep      # keep the csv pages; one .ncu-rep (c4) is enough to bring back
+rm -f $OUT/c3_full.ncu-rep $OUT/c5lite_full.ncu-rep $OUT/c5_full.ncu-rep      # keep the csv pages; one .ncu-rep (c4) is enough to bring back
+# 4. DRAM traffic of the captured EXTEND launch per configuration (bench.py: roofline.traffic)
+python - <<PY
+import json, sys
+sys.path.insert(0, "tools")
+from ncu_digest import digest
+out = {}
+for tag in ("c3", "c4", "c5lite", "c5"):
+    try:
+        recs = digest("$OUT/%s_full_raw.csv" % tag)
+        stats = [json.loads(l[6:]) for l in open("$OUT/%s_plain.log" % tag) if l.startswith("STATS ")][-1]
+        for r in recs:
+            if "extend" in r["kernel"]:
+                out[tag] = {"dram_bytes_per_launch": r["dram_read"] + r["dram_write"], "launch_us": r["time_us"],
+                            "rays_per_launch": stats["rays"] / max(1, stats["extend_launches"]),
+                            "l2_hit_pct": r.get("l2_hit_pct"), "l1_hit_pct": r.get("l1_hit_pct"), "ipc_active": r.get("ipc_active"),
+                            "lanes_per_inst": r.get("lanes_per_inst"),
+                            "source": "ncu --set full, one steady-state k_wf_extend launch, one pool of 6 Mi slots ($TAG)"}
+    except Exception as e:
+        out[tag] = {"error": str(e)}
+json.dump(out, open("$OUT/traffic.json", "w"), indent=1)
+print(json.dumps(out))
+PY

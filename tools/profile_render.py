@@ -41,3 +41,6 @@ for _ in range(a.reps):
 print("ms %.3f  Msamples/s %.1f  Mrays/s %.1f  rays/sample %.3f | extend %.2f sort %.2f shade %.2f ms, %d launches" % (
     st["device_ms"], st["samples"] / st["device_ms"] / 1e3, st["rays"] / st["device_ms"] / 1e3, st["rays"] / st["samples"],
     st["extend_ms"], st["sort_ms"], st["shade_ms"], st["kernel_launches"]))
+import json
+print("STATS " + json.dumps({"rays": st["rays"], "samples": st["samples"], "extend_launches": st.get("extend_launches", 0),
+                            "extend_ms": st["extend_ms"], "shade_ms": st["shade_ms"], "sort_ms": st["sort_ms"], "device_ms": st["device_ms"]}))
