@@ -393,6 +393,8 @@ class FrameJob:
         env = self.env
         ok = 1.0
         try:
+            if os.environ.get("ORT_BENCH_REDUCE", "") == "nccl":
+                raise RuntimeError("ORT_BENCH_REDUCE=nccl")          # evidence runs: force the library collective
             for b in range(2):
                 handles = env.gather_bytes(self.scene.accum_ipc_export(self.acc[b]))
                 if env.rank == 0:
