@@ -278,3 +278,40 @@ def test_divergences_from_the_live_reference_are_only_its_culling_leaks(ort, ref
     same = np.ones(n, bool); same[diff] = False
     assert np.array_equal(g["mat"][same], a["mat"][same]) and np.array_equal(bits(g["normal"][same]), bits(a["normal"][same]))
     sc.close(); osc.close()
+
+
+# ----------------------------------------------------------------------------------------------- C5, full size
+def test_c5_full_size_rays_vs_oracle_and_exhaustive_kernel(ort, oracle, data_dir):
+    """BASELINE config 5 at FULL size: 729 baked bunnies = 50 629 779 triangles, 3.2 GB of nodes and records built on
+    the device from the shape lists.  The reference itself cannot load this scene (100-mesh limit, fixed arenas), but its
+    algorithm can be run on it: the product's host code builds the reference's depth-10 octree (bit-identical to the
+    reference's on every scene both can load, tests/test_host_scene.py) and the oracle -- pinned to the reference --
+    traverses it.  A CPU ray costs ~10 ms on that octree, so the subsample is stated: 320 primaries + 320 incoherent rays
+    rank- and t-exact against the oracle; 20 000 more against the exhaustive GPU kernel (all 50.6 M records per ray)."""
+    import torch
+    scn = scene_path("c5_bunny_grid_729")
+    hs = ort.HostScene.load(scn, data_dir, 3840, 2160)                    # with the octree: ~20 s, the oracle needs it
+    sc = ort.Scene.from_lists(hs.world, hs.lists(), 0)                    # records, ranks and BVH on the device
+    info = sc.info()
+    assert info["triangle_count"] == 729 * 69451 and sc.build_stats()["on_device"] == 1
+    osc = oracle.scene(hs.world, hs.root)
+    o1, d1 = oracle.make_camera_rays(hs.camera, ol.default_params(640, 360, 1), 1, 640 * 360)
+    sel = np.arange(0, 640 * 360, 640 * 360 // 320)[:320]
+    lo, hi = np.array(info["root_min"]), np.array(info["root_max"])
+    o2, d2 = oracle.make_random_rays(lo + 0.2, hi - 0.2, 2, 320)
+    O, D = np.concatenate([o1[sel], o2]), np.concatenate([d1[sel], d2])
+    r = osc.raycast(O, D, mode=0, threads=NCPU)
+    assert_hits_equal(sc.raycast_batch(O, D), r, "C5 full subsample")
+    assert (r["rank"] != 0xFFFFFFFF).all()
+    osc.close()
+    n = 20_000
+    o3, d3 = oracle.make_random_rays(lo + 0.2, hi - 0.2, 5, n)
+    dev = torch.device("cuda:0")
+    to, td = torch.from_numpy(o3).to(dev), torch.from_numpy(d3).to(dev)
+    ta, tb = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    ra, rb = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev)
+    sc.raycast_batch_device(n, to.data_ptr(), td.data_ptr(), ta.data_ptr(), ra.data_ptr())
+    sc.raycast_brute_device(n, to.data_ptr(), td.data_ptr(), tb.data_ptr(), rb.data_ptr())
+    torch.cuda.synchronize()
+    assert bool((ra == rb).all()) and bool((ta.view(torch.int32) == tb.view(torch.int32)).all())
+    sc.close(); hs.close()
