@@ -83,7 +83,15 @@ int ort_measure_l2_bandwidth(int device, uint32_t buffer_mib, float *gb_per_s);
  * ort_selftest_bsdf: materials as 10 floats (Kd, Ks, Kt, ior); per case sample_brdf
  * from `state` (-> wi, is_transmission, state after), pdf_brdf and eval_scattering
  * of (N, wi, wo).  All pointers are HOST pointers.
+ * ort_selftest_rng: the xorshift of code/random.h:5-117 on the device -- per seed 64 successive states, then (each
+ * restarting from the seed) 8 x random_between_0_1, 8 x random_between(0, between_hi), 8 x
+ * random_between_u32(0, u32_one_past_max).  ort_selftest_light_pick: n successive sample_random_lights calls
+ * (code/ray.cpp:537-601; one byte per light-list entry: is it a sphere) -- the state after each.  All integer: exact.
  * ---------------------------------------------------------------------- */
+int ort_selftest_rng(int device, uint32_t n, const uint32_t *seeds, float between_hi, uint32_t u32_one_past_max,
+                     uint32_t *states64, float *f01_8, float *between_8, uint32_t *u32_8);
+int ort_selftest_light_pick(int device, uint32_t light_count, const uint8_t *light_is_sphere, uint32_t state, uint32_t n,
+                            uint32_t *states_out);
 int ort_selftest_intersect(int device, uint32_t kind, uint32_t n, const float *cases, float *out);
 int ort_selftest_bsdf(int device, uint32_t n, const float *mat10, const float *N, const float *wo, const float *wi,
                       const uint32_t *state, const float *dist, float roughness,

@@ -153,6 +153,9 @@ def lib(path=None):
         L.ort_bake_mesh.argtypes = [C.c_int, c_u32, vp, vp, c_f, c_f, V4, V3, C.POINTER(V3), C.POINTER(V3)]
     L.ort_measure_l2_bandwidth.argtypes = [C.c_int, c_u32, C.POINTER(c_f)]
     L.ort_selftest_intersect.argtypes = [C.c_int, c_u32, c_u32, vp, vp]
+    if hasattr(L, "ort_selftest_rng"):
+        L.ort_selftest_rng.argtypes = [C.c_int, c_u32, vp, c_f, c_u32, vp, vp, vp, vp]
+        L.ort_selftest_light_pick.argtypes = [C.c_int, c_u32, vp, c_u32, c_u32, vp]
     L.ort_selftest_bsdf.argtypes = [C.c_int, c_u32, vp, vp, vp, vp, vp, vp, c_f, vp, vp, vp, vp, vp]
     L.ort_generate_camera_rays_device.argtypes = [C.c_int, vp, C.POINTER(RenderParams), c_u32, c_u64, vp, vp, vp]
     L.ort_generate_random_rays_device.argtypes = [C.c_int, C.POINTER(c_f), C.POINTER(c_f), c_u32, c_u64, vp, vp, vp]
@@ -231,6 +234,37 @@ def selftest_intersect(kind, cases, device=0):
     out = np.zeros((a.shape[0], 5), np.float32)
     _check(lib().ort_selftest_intersect(device, k, a.shape[0], _ptr(a), _ptr(out)))
     return out
+
+
+def selftest_rng(seeds, between_hi=6.2831855, u32_one_past_max=12, device=0):
+    """the DEVICE xorshift (code/random.h): (states [n, 64], f01 [n, 8], between [n, 8], u32 [n, 8]) per seed"""
+    s = np.ascontiguousarray(seeds, np.uint32).reshape(-1)
+    n = s.shape[0]
+    st = np.zeros((n, 64), np.uint32); f01 = np.zeros((n, 8), np.float32)
+    bt = np.zeros((n, 8), np.float32); u = np.zeros((n, 8), np.uint32)
+    _check(lib().ort_selftest_rng(device, n, _ptr(s), c_f(between_hi), u32_one_past_max, _ptr(st), _ptr(f01), _ptr(bt), _ptr(u)))
+    return st, f01, bt, u
+
+
+def selftest_light_pick(light_is_sphere, state, n, device=0):
+    """n successive sample_random_lights calls on the DEVICE: the RNG state after each"""
+    l = np.ascontiguousarray(light_is_sphere, np.uint8).reshape(-1)
+    out = np.zeros(n, np.uint32)
+    _check(lib().ort_selftest_light_pick(device, l.shape[0], _ptr(l), state, n, _ptr(out)))
+    return out
+
+
+def world_light_is_sphere(world_ptr):
+    """decodes World.light_push_buffer (packed (u32 ShapeType, pointer) pairs, parser.cpp:1144-1182): 1 per sphere entry"""
+    base = C.cast(_as_ptr(world_ptr), C.POINTER(C.c_uint8))
+    raw = bytes(base[40:80])
+    import struct
+    _arena, buf, _total, used = struct.unpack("<QQQQ", raw[:32])
+    count = struct.unpack("<I", raw[32:36])[0]
+    data = C.string_at(buf, used) if buf and used else b""
+    out = [1 if struct.unpack_from("<I", data, 12 * k)[0] == 1 else 0 for k in range(len(data) // 12)]
+    assert len(out) == count
+    return np.array(out, np.uint8)
 
 
 def selftest_bsdf(mat10, N, wo, wi, state, dist, roughness=0.01, device=0):

@@ -109,6 +109,30 @@ __global__ void k_st_bsdf(uint32_t n, const q4 *__restrict__ materials, const fl
     eval[3 * i] = e.x; eval[3 * i + 1] = e.y; eval[3 * i + 2] = e.z;
 }
 
+
+// RNG (code/random.h) on the device: per seed 64 xorshift states, then -- each from the seed again -- 8 x
+// random_between_0_1, 8 x random_between(0, hi), 8 x random_between_u32(0, n)
+__global__ void k_st_rng(uint32_t n, const uint32_t *__restrict__ seeds, float hi, uint32_t one_past_max,
+                         uint32_t *__restrict__ states, float *__restrict__ f01, float *__restrict__ between, uint32_t *__restrict__ u32)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    uint32_t x = seeds[i];
+    for(int k = 0; k < 64; ++k) { xor_shift_32(&x); states[64u * i + k] = x; }
+    x = seeds[i];
+    for(int k = 0; k < 8; ++k) f01[8u * i + k] = random_between_0_1(&x);
+    x = seeds[i];
+    for(int k = 0; k < 8; ++k) between[8u * i + k] = random_between(&x, 0.0f, hi);
+    x = seeds[i];
+    for(int k = 0; k < 8; ++k) u32[8u * i + k] = random_between_u32(&x, 0u, one_past_max);
+}
+// sample_random_lights (ray.cpp:537-601) as the render kernels run it: only its RNG side effects survive
+__global__ void k_st_light_pick(uint32_t n, PathConsts pc, uint32_t state, uint32_t *__restrict__ out)
+{
+    if(blockIdx.x != 0 || threadIdx.x != 0) return;
+    for(uint32_t k = 0; k < n; ++k) { sample_random_lights_rng(pc, &state); out[k] = state; }
+}
+
 // ---- ray buffers of BASELINE config 2 ---------------------------------------------------------------
 // ray i draws from its own xorshift stream ort_stream_seed(seed, i, 0).  Coherent: pixel (i % w, i / w) of a
 // w x h grid, lens sample as ray.cpp:1232-1237 (generate_primary of path.h, the render kernels' own code).
@@ -331,6 +355,48 @@ int ort_selftest_bsdf(int device, uint32_t n, const float *mat10, const float *N
     ORT_GUARD_END
 }
 
+
+int ort_selftest_rng(int device, uint32_t n, const uint32_t *seeds, float between_hi, uint32_t u32_one_past_max,
+                     uint32_t *states64, float *f01_8, float *between_8, uint32_t *u32_8)
+{
+    ORT_GUARD_BEGIN
+    if(n && (!seeds || !states64 || !f01_8 || !between_8 || !u32_8)) return fail_with(ORT_ERR_ARG, "null argument");
+    if(u32_one_past_max == 0) return fail_with(ORT_ERR_ARG, "u32_one_past_max must be > 0");
+    int rc = pick_device(device);
+    if(rc != ORT_OK) return rc;
+    if(n == 0) return ORT_OK;
+    DevBuf d_s, d_st, d_f, d_b, d_u;
+    ORT_CUDA_TRY(d_s.alloc(n * 4)); ORT_CUDA_TRY(d_st.alloc((size_t)n * 64 * 4)); ORT_CUDA_TRY(d_f.alloc((size_t)n * 8 * 4));
+    ORT_CUDA_TRY(d_b.alloc((size_t)n * 8 * 4)); ORT_CUDA_TRY(d_u.alloc((size_t)n * 8 * 4));
+    ORT_CUDA_TRY(cudaMemcpy(d_s.p, seeds, n * 4, cudaMemcpyHostToDevice));
+    k_st_rng<<<(n + 63u) / 64u, 64>>>(n, d_s.as<uint32_t>(), between_hi, u32_one_past_max, d_st.as<uint32_t>(), d_f.as<float>(), d_b.as<float>(), d_u.as<uint32_t>());
+    ORT_CUDA_TRY(cudaGetLastError());
+    ORT_CUDA_TRY(cudaMemcpy(states64, d_st.p, (size_t)n * 64 * 4, cudaMemcpyDeviceToHost));
+    ORT_CUDA_TRY(cudaMemcpy(f01_8, d_f.p, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
+    ORT_CUDA_TRY(cudaMemcpy(between_8, d_b.p, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
+    ORT_CUDA_TRY(cudaMemcpy(u32_8, d_u.p, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
+    return ORT_OK;
+    ORT_GUARD_END
+}
+
+int ort_selftest_light_pick(int device, uint32_t light_count, const uint8_t *light_is_sphere, uint32_t state, uint32_t n, uint32_t *states_out)
+{
+    ORT_GUARD_BEGIN
+    if((light_count && !light_is_sphere) || (n && !states_out)) return fail_with(ORT_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if(rc != ORT_OK) return rc;
+    if(n == 0) return ORT_OK;
+    DevBuf d_l, d_o;
+    ORT_CUDA_TRY(d_l.alloc(light_count)); ORT_CUDA_TRY(d_o.alloc((size_t)n * 4));
+    if(light_count) ORT_CUDA_TRY(cudaMemcpy(d_l.p, light_is_sphere, light_count, cudaMemcpyHostToDevice));
+    PathConsts pc; memset(&pc, 0, sizeof(pc));
+    pc.light_count = light_count; pc.light_is_sphere = d_l.as<uint8_t>();
+    k_st_light_pick<<<1, 32>>>(n, pc, state, d_o.as<uint32_t>());
+    ORT_CUDA_TRY(cudaGetLastError());
+    ORT_CUDA_TRY(cudaMemcpy(states_out, d_o.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return ORT_OK;
+    ORT_GUARD_END
+}
 
 int ort_bake_mesh(int device, uint32_t vertex_count, const ort_v3 *vertices_in, ort_v3 *vertices_out,
                   float scale, float degree, ort_v4 quaternion, ort_v3 translate, ort_v3 *aabb_min, ort_v3 *aabb_max)

@@ -81,6 +81,35 @@ def test_intersectors_random_cases_vs_oracle_on_device(ort, oracle):
     assert ort.selftest_intersect("triangle", np.zeros((0, 15), np.float32)).shape == (0, 5)     # empty batch
 
 
+def test_rng_golden_on_device(ort, gold):
+    """a11: xor_shift_32 (third shift is a RIGHT shift), random_between_0_1 = x / 2^32 in [0, 1], random_between (two
+    steps), random_between_u32 -- states and float bits equal to the reference's, on the device"""
+    st, f01, bt, u = ort.selftest_rng(gold["rng_seeds"], 6.2831855, 12)
+    assert np.array_equal(st, gold["rng_states"])
+    assert np.array_equal(bits(f01), bits(gold["rng_f01"]))
+    assert np.array_equal(bits(bt), bits(gold["rng_between"]))
+    assert np.array_equal(u, gold["rng_u32_12"])
+    # the survey's known answer (SURVEY.md 8a, a11) and the absorbing state
+    st, f01, _, _ = ort.selftest_rng([12345, 0])
+    assert list(st[0, :4]) == [104278947, 3831047122, 3324124125, 2171811514]
+    assert abs(float(f01[0, 0]) - 0.0242793337) < 1e-9 and not st[1].any()
+
+
+def test_light_pick_rng_golden_on_device(ort, gold):
+    """a10: sample_random_lights' only surviving effect is on the RNG -- one step to pick the entry, four more when the
+    entry is a sphere (ray.cpp:537-601); the device consumes the reference's stream exactly"""
+    import oracle_lib as ol
+    hs = ort.HostScene.load(os.path.join(ol.SCENES_DIR, "box_spheres.scn"), ol.SCENES_DIR, 64, 36)
+    lights = ort.world_light_is_sphere(hs.world)
+    assert len(lights) == int(gold["scene_counts"][5]) and lights.any() and not lights.all()
+    out = ort.selftest_light_pick(lights, 99, 32)
+    assert np.array_equal(out, gold["scene_light_states"])
+    # no light at all: one step, no pick (the reference would divide by zero, random.h:80)
+    st, _, _, _ = ort.selftest_rng([99])
+    assert ort.selftest_light_pick(np.zeros(0, np.uint8), 99, 1)[0] == st[0, 0]
+    hs.close()
+
+
 def rel_err(a, b, floor):
     return np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(np.abs(b.astype(np.float64)), floor)
 
