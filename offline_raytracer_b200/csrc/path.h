@@ -94,10 +94,22 @@ struct Mat
     f3 Ed;
     uint32_t lobes;                    // bit 0/1/2: length_square(Kd/Ks/Kt) > 0
 };
+// DevMaterial is 96 bytes at a 96-byte stride from a 256-byte-aligned base: three 256-bit read-only loads on the
+// device (sm_100: LDG.E.256.CONSTANT) instead of six 128-bit ones (measured variant, profiles/README.md)
+#ifndef ORT_MAT_LD256
+#define ORT_MAT_LD256 0
+#endif
 ORT_HD Mat load_material(const PathConsts &c, uint32_t index)
 {
     const q4 *p = c.materials + 6u * index;
+#if ORT_MAT_LD256 && defined(__CUDA_ARCH__)
+    q4 a, b, t, e, k, d;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w), "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "l"(p + 2));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w), "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(p + 4));
+#else
     q4 a = ldq(p), b = ldq(p + 1), t = ldq(p + 2), e = ldq(p + 3), k = ldq(p + 4), d = ldq(p + 5);
+#endif
     Mat m;
     m.Kd = q3(a); m.is_light = (int)f2u(a.w);
     m.Ks = q3(b); m.ior = b.w;
