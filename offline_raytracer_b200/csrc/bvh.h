@@ -48,6 +48,9 @@ namespace ort {
 
 struct alignas(16) q4 { float x, y, z, w; };
 
+#ifndef ORT_NODE_PAD
+#define ORT_NODE_PAD 0
+#endif
 struct alignas(16) WideNode
 {
     float px, py, pz;
@@ -57,8 +60,16 @@ struct alignas(16) WideNode
     uint8_t qlo_x[8], qlo_y[8];
     uint8_t qlo_z[8], qhi_x[8];
     uint8_t qhi_y[8], qhi_z[8];
+#if ORT_NODE_PAD
+    uint8_t pad[16];                      // measured variant: 96-byte nodes = three aligned 32-byte sectors, fetched as 3 x 256 bits
+#endif
 };
+#if ORT_NODE_PAD
+static_assert(sizeof(WideNode) == 96, "padded WideNode is 6 x 16 B");
+#else
 static_assert(sizeof(WideNode) == 80, "WideNode is 5 x 16 B");
+#endif
+#define ORT_NODE_QUADS ((uint32_t)(sizeof(WideNode) / 16u))
 
 struct alignas(16) PrimRec
 {
@@ -267,8 +278,16 @@ ORT_HD void trav_visit(const SceneView &s, T &t, Stack &st, float clip_t, TraceC
     uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
     const uint32_t node_index = t.ng_x + rel;
     const float t_clip = (node_index >= s.main_root) ? clip_t : FLT_MAX;
-    const q4 *np = s.nodes + 5u * node_index;
+    const q4 *np = s.nodes + ORT_NODE_QUADS * node_index;
+#if ORT_NODE_PAD && defined(__CUDA_ARCH__)
+    q4 n0, n1, n2, n3, n4, n5;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(np + 2));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(n4.x), "=f"(n4.y), "=f"(n4.z), "=f"(n4.w), "=f"(n5.x), "=f"(n5.y), "=f"(n5.z), "=f"(n5.w) : "l"(np + 4));
+    (void)n5;
+#else
     q4 n0 = ldq(np), n1 = ldq(np + 1), n2 = ldq(np + 2), n3 = ldq(np + 3), n4 = ldq(np + 4);
+#endif
     if(COUNT == 1) cnt->node_visits++;
 
     uint32_t e_imask = f2u(n0.w);

@@ -8,7 +8,7 @@ for spec in "$@"; do
     name="${spec%%=*}"; flags="${spec#*=}"
     rm -rf "vb_$name"; mkdir "vb_$name"
     cp csrc/*.cu csrc/*.cuh csrc/*.h csrc/*.cpp csrc/Makefile "vb_$name"/
-    ( cd "vb_$name" && make -s OUT="../variants/$name.so" EXTRA_NVFLAGS="$flags" >/dev/null 2>"../variants/$name.log"; cp ptxas.log "../variants/$name.ptxas" 2>/dev/null; cd .. && rm -rf "vb_$name" ) &
+    ( cd "vb_$name" && make -s OUT="../variants/$name.so" EXTRA_NVFLAGS="$flags" EXTRA_CXXFLAGS="$(echo "$flags" | tr " " "\n" | grep "^-D" | tr "\n" " ")" >/dev/null 2>"../variants/$name.log"; cp ptxas.log "../variants/$name.ptxas" 2>/dev/null; cd .. && rm -rf "vb_$name" ) &
 done
 wait
 ls -la variants/*.so
