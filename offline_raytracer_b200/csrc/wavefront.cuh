@@ -173,9 +173,6 @@ __device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot,
 #ifndef ORT_EXTEND_ONE_PRIM
 #define ORT_EXTEND_ONE_PRIM 1
 #endif
-#ifndef ORT_EXTEND_STAGE
-#define ORT_EXTEND_STAGE 0
-#endif
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, ORT_EXTEND_MIN_BLOCKS)
@@ -193,43 +190,6 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
     // finish together (static ranges left SMs half empty at the end of every launch)
     uint32_t next = 0u, end = 0u;
     bool exhausted = false;
-#if ORT_EXTEND_STAGE
-    // ORT_EXTEND_STAGE: the ray sectors of the next 32 slots of the warp's stream are copied to shared
-    // memory (cp.async) at one refill and consumed at the next, so that a refill does not stall the whole
-    // warp for an HBM round trip (ncu, C4: 10 % of EXTEND's warp samples wait on that load).  The stream
-    // of a warp is a sequence q = 0, 1, 2 ... over the chunks it reserves; q lives in ring entry q & 31.
-    __shared__ float4 sh_ring[4][32][2];
-    float4 (*ring)[2] = sh_ring[threadIdx.x >> 5];
-    uint32_t cons = 0u, prod = 0u, limit = 0u, base0 = 0u, base1 = 0u;   // warp-uniform
-    bool stream_end = false;
-    (void)next; (void)end;
-    auto stage = [&]()
-    {
-        uint32_t room = 32u - (prod - cons);
-        if(!stream_end && prod + room > limit)
-        {
-            uint32_t base = 0u;
-            if(lane == 0) base = atomicAdd(chunk_counter, WF_CHUNK);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if(base >= wf.capacity) stream_end = true;
-            else { if((limit / WF_CHUNK) & 1u) base1 = base; else base0 = base; limit += WF_CHUNK; }
-        }
-        uint32_t n = limit - prod; if(n > room) n = room;
-        if(lane < n)
-        {
-            uint32_t q = prod + lane;
-            uint32_t s = (((q / WF_CHUNK) & 1u) ? base1 : base0) + (q % WF_CHUNK);
-            if(s < wf.capacity)
-            {
-                const float4 *g = wf.rec + (size_t)WF_REC_QUADS * s;
-                uint32_t d = (uint32_t)__cvta_generic_to_shared(&ring[q & 31u][0]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(g) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + 16u), "l"(g + 1) : "memory");
-            }
-        }
-        prod += n;
-    };
-#endif
 
     Trav t;
     t.ng_x = t.ng_y = 0u; t.sp = 0;
@@ -244,38 +204,6 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
     for(;;)
     {
         uint32_t idle_mask = __ballot_sync(0xFFFFFFFFu, !has_ray);
-#if ORT_EXTEND_STAGE
-        if(!exhausted && (__popc(idle_mask) >= ORT_FETCH_MIN || idle_mask == 0xFFFFFFFFu))
-        {
-            if(prod == cons) stage();                         // nothing staged yet: this one refill waits
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncwarp();
-            const uint32_t avail = prod - cons;
-            const uint32_t r = __popc(idle_mask & ((1u << lane) - 1u));
-            if(!has_ray && r < avail)
-            {
-                uint32_t q = cons + r;
-                uint32_t my = (((q / WF_CHUNK) & 1u) ? base1 : base0) + (q % WF_CHUNK);
-                if(my < wf.capacity)
-                {
-                    float4 ro = ring[q & 31u][0], rd = ring[q & 31u][1];
-                    if(wf_state_of(__float_as_uint(rd.w)) == WF_ACTIVE)
-                    {
-                        trav_init(scene, t, st, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z));
-                        is_primary = __float_as_uint(rd.w) >> 31;
-                        slot = my;
-                        has_ray = true;
-                        ++rays;
-                    }
-                    else { wf.key[my] = WF_KEY_DEAD; atomicAdd(&sh_hist[WF_KEY_DEAD], 1u); }
-                }
-            }
-            cons += min((uint32_t)__popc(idle_mask), avail);
-            __syncwarp();                                     // every entry read before it is overwritten
-            stage();
-            exhausted = stream_end && prod == cons;
-        }
-#else
         if(!exhausted && (__popc(idle_mask) >= ORT_FETCH_MIN || idle_mask == 0xFFFFFFFFu))
         {
             if(next >= end)
@@ -306,7 +234,6 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
             next += __popc(idle_mask);
             if(next > end) next = end;
         }
-#endif
         if(__ballot_sync(0xFFFFFFFFu, has_ray) == 0u)
         {
             if(exhausted) break;
