@@ -217,7 +217,7 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
         s->wf_ready = 1;
     }
     if(s->wf.capacity >= capacity) return ORT_OK;
-    cudaFree(s->wf.rec); cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->wf.cold); cudaFree(s->wf.rmask);
+    cudaFree(s->wf.rec); cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->wf.cold);
     memset(&s->wf, 0, sizeof(s->wf));
     CUDA_TRY(cudaMalloc((void **)&s->wf.rec, (size_t)capacity * WF_REC_QUADS * sizeof(float4)));
 #if WF_SPLIT_COLD
@@ -225,9 +225,6 @@ int ensure_wavefront(OrtScene *s, uint32_t capacity)
 #endif
     CUDA_TRY(cudaMalloc((void **)&s->wf.key, (size_t)capacity * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&s->wf.perm, (size_t)capacity * sizeof(uint32_t)));
-#if ORT_SHADE_SPLIT
-    CUDA_TRY(cudaMalloc((void **)&s->wf.rmask, ((size_t)capacity / 32u + 32u) * sizeof(uint32_t)));
-#endif
     s->wf.capacity = capacity;
     return ORT_OK;
 }
@@ -275,7 +272,6 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         pl.wf.cold = s->wf.cold ? s->wf.cold + 2ull * lo : 0;
         pl.wf.key = s->wf.key + lo;
         pl.wf.perm = s->wf.perm + lo;
-        pl.wf.rmask = s->wf.rmask ? s->wf.rmask + lo / 32u : 0;
         pl.wf.capacity = hi - lo;
         pl.cur = 0; pl.finished = pl.wf.capacity == 0;
         CUDA_TRY(cudaStreamWaitEvent(pl.stream, s->wf_start, 0));
@@ -312,10 +308,6 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
             }
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][2], st));
             k_wf_shade<<<grid, 128, 0, st>>>(a, pl.wf, act + it, live, sorted);
-#if ORT_SHADE_SPLIT
-            k_wf_regen<<<(cap + 1023u) / 1024u, 256, 0, st>>>(a, pl.wf, act + it, sorted);
-            *launches += 1;
-#endif
             CUDA_TRY(cudaEventRecord(pl.ev[b][it][3], st));
         }
         *launches += 2 * WF_BATCH;
@@ -348,10 +340,6 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         k_wf_reset<<<grid, 128, 0, pl.stream>>>(pl.wf);
         CUDA_TRY(cudaMemsetAsync(pl.d_active, 0, 2 * WF_BATCH * sizeof(unsigned int), pl.stream));
         k_wf_shade<<<grid, 128, 0, pl.stream>>>(a, pl.wf, pl.d_active, pl.d_sort + 2 * WF_KEY_BINS, 0);
-#if ORT_SHADE_SPLIT
-        k_wf_regen<<<(pl.wf.capacity + 1023u) / 1024u, 256, 0, pl.stream>>>(a, pl.wf, pl.d_active, 0);
-        *launches += 1;
-#endif
         *launches += 2;
         rc = enqueue(pl, 0);
         if(rc != ORT_OK) return rc;
@@ -783,7 +771,7 @@ int ort_scene_destroy(OrtScene *s)
             }
         }
     }
-    cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->wf.cold); cudaFree(s->wf.rmask); cudaFree(s->d_sort);
+    cudaFree(s->wf.key); cudaFree(s->wf.perm); cudaFree(s->wf.cold); cudaFree(s->d_sort);
     if(s->h_active) cudaFreeHost(s->h_active);
     if(s->ev0) cudaEventDestroy(s->ev0);
     if(s->ev1) cudaEventDestroy(s->ev1);

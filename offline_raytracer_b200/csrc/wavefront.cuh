@@ -65,7 +65,6 @@ struct WfBuffers
     float4 *cold;        // WF_SPLIT_COLD: q4, q5 of every slot (2 quads per slot); else unused
     uint32_t *key;       // shading key written by EXTEND: primary << 8 | min(material, 254); 511 = dead (so 256 | 255 must never be a live key)
     uint32_t *perm;      // slots grouped by key (counting sort)
-    uint32_t *rmask;     // ORT_SHADE_SPLIT: bit j = the path handled by SHADE thread j ended (one word per warp)
     uint32_t capacity;
 };
 
@@ -111,7 +110,6 @@ __global__ void k_wf_reset(WfBuffers wf)
     {
         float4 *rec = wf.rec + (size_t)WF_REC_QUADS * i;
         rec[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(wf_flags(WF_FRESH, false)));
-        rec[2] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));      // no radiance, no series (what k_wf_regen reads)
         rec[3] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_PIXEL_MASK | wf_flags(WF_FRESH, false)));
         float4 *cold = wf_cold(wf, i);
         cold[0] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
@@ -174,10 +172,6 @@ __device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot,
 // C3 170.0 -> 167.9, testscene 71.3 -> 70.5, 4.4 M-triangle grid 229.6 -> 208.7)
 #ifndef ORT_EXTEND_ONE_PRIM
 #define ORT_EXTEND_ONE_PRIM 1
-#endif
-// ORT_SHADE_SPLIT: the regeneration of ended paths (phase 2 of SHADE) as a kernel of its own, k_wf_regen
-#ifndef ORT_SHADE_SPLIT
-#define ORT_SHADE_SPLIT 0
 #endif
 
 template <bool COUNT>
@@ -416,99 +410,13 @@ struct WfRegen           // what phase 2 needs to know about a slot whose path e
     uint32_t series, pixel_index, slot, pad0, pad1;
 };
 
-// Phase 2 of SHADE for one slot whose path ended: ACCUMULATE the finished stream, pull the next one,
-// GENERATE the camera ray (ray.cpp:1215-1246, 1428).
-__device__ __forceinline__ void wf_regenerate(const RenderArgs &a, const WfBuffers &wf, const WfRegen &rg,
-                                              unsigned long long &n_samples, unsigned int &still_active)
-{
-    float4 *rec = wf.rec + (size_t)WF_REC_QUADS * rg.slot;
-    float4 *cold = wf_cold(wf, rg.slot);
-    float4 scol, sch;                                   // the third sector: only paths that end touch it
-    wf_ld2(cold, scol, sch);
-    f3 color = mk3(scol.x, scol.y, scol.z) + mk3(rg.dx, rg.dy, rg.dz);
-    uint32_t samples_left = __float_as_uint(scol.w), pixel_index = rg.pixel_index, chunk = __float_as_uint(sch.x);
-    Path p;
-    p.series = rg.series;
-    bool dead = false;
-    if(samples_left == 0)
-    {
-        // ---- accumulate the finished stream (ray.cpp:1428) ----
-        if(pixel_index != WF_PIXEL_MASK)
-        {
-            if(a.accum)
-            {
-                unsigned long long *dst = (unsigned long long *)(a.accum + 4ull * pixel_index);
-                atomicAdd(dst + 0, (unsigned long long)to_fixed(color.x));
-                atomicAdd(dst + 1, (unsigned long long)to_fixed(color.y));
-                atomicAdd(dst + 2, (unsigned long long)to_fixed(color.z));
-            }
-            else
-            {
-                f3 px = color / (float)a.spp;
-                a.rgb[3ull * pixel_index + 0] = px.x;
-                a.rgb[3ull * pixel_index + 1] = px.y;
-                a.rgb[3ull * pixel_index + 2] = px.z;
-            }
-        }
-        // ---- next stream from the global work counter ----
-        int x = -1, y = -1;
-        for(;;)
-        {
-            unsigned long long item = atomicAdd(a.work_counter, 1ull);
-            if(item >= a.total_items) break;
-            uint32_t lane = (uint32_t)(item & 31ull);
-            unsigned long long blk = item >> 5;
-            uint32_t bx = (uint32_t)(blk % a.blocks_x); blk /= a.blocks_x;
-            uint32_t by = (uint32_t)(blk % a.blocks_y); blk /= a.blocks_y;
-            int lx = (int)(bx * 8u + (lane & 7u)), ly = (int)(by * 4u + (lane >> 3));
-            if(lx < a.tile_w && ly < a.tile_h)
-            {
-                x = a.tile_min_x + lx; y = a.tile_min_y + ly;
-                chunk = a.chunk_begin + (uint32_t)blk;
-                break;
-            }
-        }
-        if(x < 0) dead = true;
-        else
-        {
-            pixel_index = (uint32_t)(y * a.pc.width + x);
-            samples_left = a.chunk_spp;
-            if((chunk + 1u) * a.chunk_spp > a.spp) samples_left = a.spp - chunk * a.chunk_spp;
-            p.series = ort_stream_seed(a.base_seed, pixel_index, chunk);
-            color = mk3(0.f, 0.f, 0.f);
-        }
-    }
-    if(dead)
-    {
-        rec[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(wf_flags(WF_DEAD, false)));
-        rec[3] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_PIXEL_MASK | wf_flags(WF_DEAD, false)));
-    }
-    else
-    {
-        // ---- generate (ray.cpp:1215-1246) ----
-        int x = (int)(pixel_index % (uint32_t)a.pc.width), y = (int)(pixel_index / (uint32_t)a.pc.width);
-        generate_primary(a.pc, pixel_focal_point(a.pc, x, y), &p);
-        --samples_left;
-        n_samples = 1;
-        wf_st2(rec, make_float4(p.origin.x, p.origin.y, p.origin.z, 0.f),
-               make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(wf_flags(WF_ACTIVE, true))));
-        wf_st2(rec + 2, make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series)),
-               make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index | wf_flags(WF_ACTIVE, true))));
-        wf_st2(cold, make_float4(color.x, color.y, color.z, __uint_as_float(samples_left)),
-               make_float4(__uint_as_float(chunk), 0.f, 0.f, 0.f));
-        still_active += 1;
-    }
-}
-
 __global__ void __launch_bounds__(128, ORT_SHADE_MIN_BLOCKS)
 k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uint32_t *live, int sorted)
 {
-#if !ORT_SHADE_SPLIT
     __shared__ WfRegen sh_regen[128];
     __shared__ uint32_t sh_count;
     if(threadIdx.x == 0) sh_count = 0u;
     __syncthreads();
-#endif
 
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n_samples = 0;
@@ -560,27 +468,12 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
             else
             {
                 regen = true;
-#if ORT_SHADE_SPLIT
-                // what k_wf_regen needs of an ended path, in the sector it will overwrite anyway
-                wf_st2(rec + 2, make_float4(delta.x, delta.y, delta.z, __uint_as_float(p.series)),
-                       make_float4(0.f, 0.f, 0.f, __uint_as_float(pixel_index | wf_flags(WF_ACTIVE, false))));
-#else
                 rg.dx = delta.x; rg.dy = delta.y; rg.dz = delta.z;
                 rg.series = p.series; rg.pixel_index = pixel_index;
-#endif
             }
         }
-        else if(state == WF_FRESH) regen = true;      // no stream yet: samples left 0, no pixel (k_wf_reset wrote that sector)
+        else if(state == WF_FRESH) regen = true;      // no stream yet: samples left 0, no pixel
     }
-#if ORT_SHADE_SPLIT
-    // one mask word per warp tells k_wf_regen which threads' slots to regenerate: no barrier, no atomic, the
-    // block leaves as soon as its slowest warp has shaded
-    {
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, regen);
-        if((threadIdx.x & 31u) == 0u) wf.rmask[j >> 5] = m;
-    }
-    (void)rg;
-#else
     // ---- compaction of the slots to regenerate ----
     {
         const uint32_t lane = threadIdx.x & 31u;
@@ -595,69 +488,83 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
     if(threadIdx.x < sh_count)
     {
         rg = sh_regen[threadIdx.x];
-        wf_regenerate(a, wf, rg, n_samples, still_active);
-    }
-#endif
-    n_samples = warp_sum(n_samples);
-    still_active = __reduce_add_sync(0xFFFFFFFFu, still_active);
-    if((threadIdx.x & 31) == 0)
-    {
-        if(n_samples) atomicAdd(&a.stats[STAT_SAMPLES], n_samples);
-        if(still_active) atomicAdd(active_out, still_active);
-    }
-}
-
-#if ORT_SHADE_SPLIT
-// Phase 2 as a kernel of its own.  Inside k_wf_shade one warp of four regenerated while the block's other
-// three had nothing left to do but kept their registers (ncu, C4: the block spent ~45 % of its life that way,
-// and 15 % of all warp samples sat at the barrier in front of it).  Here a block of 256 threads takes the mask
-// words of 1024 SHADE threads, compacts the set bits in shared memory and regenerates with full warps.
-__global__ void __launch_bounds__(256)
-k_wf_regen(const RenderArgs a, WfBuffers wf, unsigned int *active_out, int sorted)
-{
-    __shared__ uint32_t sh_mask[32], sh_pref[33];
-    __shared__ uint16_t sh_pos[1024];
-    const uint32_t tile = blockIdx.x * 1024u;
-    const uint32_t words = (wf.capacity + 31u) / 32u;
-    if(threadIdx.x < 32u)
-    {
-        uint32_t w = tile / 32u + threadIdx.x;
-        uint32_t m = w < words ? wf.rmask[w] : 0u;
-        uint32_t c = (uint32_t)__popc(m), incl = c;
-#pragma unroll
-        for(uint32_t o = 1; o < 32u; o <<= 1)
+        float4 *rec = wf.rec + (size_t)WF_REC_QUADS * rg.slot;
+        float4 *cold = wf_cold(wf, rg.slot);
+        float4 scol, sch;                                   // the third sector: only paths that end touch it
+        wf_ld2(cold, scol, sch);
+        f3 color = mk3(scol.x, scol.y, scol.z) + mk3(rg.dx, rg.dy, rg.dz);
+        uint32_t samples_left = __float_as_uint(scol.w), pixel_index = rg.pixel_index, chunk = __float_as_uint(sch.x);
+        Path p;
+        p.series = rg.series;
+        bool dead = false;
+        if(samples_left == 0)
         {
-            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if(threadIdx.x >= o) incl += v;
+            // ---- accumulate the finished stream (ray.cpp:1428) ----
+            if(pixel_index != WF_PIXEL_MASK)
+            {
+                if(a.accum)
+                {
+                    unsigned long long *dst = (unsigned long long *)(a.accum + 4ull * pixel_index);
+                    atomicAdd(dst + 0, (unsigned long long)to_fixed(color.x));
+                    atomicAdd(dst + 1, (unsigned long long)to_fixed(color.y));
+                    atomicAdd(dst + 2, (unsigned long long)to_fixed(color.z));
+                }
+                else
+                {
+                    f3 px = color / (float)a.spp;
+                    a.rgb[3ull * pixel_index + 0] = px.x;
+                    a.rgb[3ull * pixel_index + 1] = px.y;
+                    a.rgb[3ull * pixel_index + 2] = px.z;
+                }
+            }
+            // ---- next stream from the global work counter ----
+            int x = -1, y = -1;
+            for(;;)
+            {
+                unsigned long long item = atomicAdd(a.work_counter, 1ull);
+                if(item >= a.total_items) break;
+                uint32_t lane = (uint32_t)(item & 31ull);
+                unsigned long long blk = item >> 5;
+                uint32_t bx = (uint32_t)(blk % a.blocks_x); blk /= a.blocks_x;
+                uint32_t by = (uint32_t)(blk % a.blocks_y); blk /= a.blocks_y;
+                int lx = (int)(bx * 8u + (lane & 7u)), ly = (int)(by * 4u + (lane >> 3));
+                if(lx < a.tile_w && ly < a.tile_h)
+                {
+                    x = a.tile_min_x + lx; y = a.tile_min_y + ly;
+                    chunk = a.chunk_begin + (uint32_t)blk;
+                    break;
+                }
+            }
+            if(x < 0) dead = true;
+            else
+            {
+                pixel_index = (uint32_t)(y * a.pc.width + x);
+                samples_left = a.chunk_spp;
+                if((chunk + 1u) * a.chunk_spp > a.spp) samples_left = a.spp - chunk * a.chunk_spp;
+                p.series = ort_stream_seed(a.base_seed, pixel_index, chunk);
+                color = mk3(0.f, 0.f, 0.f);
+            }
         }
-        sh_mask[threadIdx.x] = m;
-        sh_pref[threadIdx.x] = incl - c;
-        if(threadIdx.x == 31u) sh_pref[32] = incl;
-    }
-    __syncthreads();
-    const uint32_t count = sh_pref[32];
-    if(count == 0u) return;
-#pragma unroll
-    for(uint32_t k = 0; k < 4u; ++k)
-    {
-        uint32_t pos = threadIdx.x + 256u * k;
-        uint32_t m = sh_mask[pos >> 5], b = pos & 31u;
-        if((m >> b) & 1u) sh_pos[sh_pref[pos >> 5] + (uint32_t)__popc(m & ((1u << b) - 1u))] = (uint16_t)pos;
-    }
-    __syncthreads();
-    unsigned long long n_samples = 0;
-    unsigned int still_active = 0;
-    for(uint32_t e = threadIdx.x; e < count; e += 256u)
-    {
-        uint32_t j = tile + sh_pos[e];
-        WfRegen rg;
-        rg.slot = sorted ? wf.perm[j] : j;
-        float4 q2, q3;
-        wf_ld2(wf.rec + (size_t)WF_REC_QUADS * rg.slot + 2, q2, q3);
-        rg.dx = q2.x; rg.dy = q2.y; rg.dz = q2.z; rg.series = __float_as_uint(q2.w);
-        rg.pixel_index = __float_as_uint(q3.w) & WF_PIXEL_MASK;
-        rg.pad0 = rg.pad1 = 0u;
-        wf_regenerate(a, wf, rg, n_samples, still_active);
+        if(dead)
+        {
+            rec[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(wf_flags(WF_DEAD, false)));
+            rec[3] = make_float4(0.f, 0.f, 0.f, __uint_as_float(WF_PIXEL_MASK | wf_flags(WF_DEAD, false)));
+        }
+        else
+        {
+            // ---- generate (ray.cpp:1215-1246) ----
+            int x = (int)(pixel_index % (uint32_t)a.pc.width), y = (int)(pixel_index / (uint32_t)a.pc.width);
+            generate_primary(a.pc, pixel_focal_point(a.pc, x, y), &p);
+            --samples_left;
+            n_samples = 1;
+            wf_st2(rec, make_float4(p.origin.x, p.origin.y, p.origin.z, 0.f),
+                   make_float4(p.dir.x, p.dir.y, p.dir.z, __uint_as_float(wf_flags(WF_ACTIVE, true))));
+            wf_st2(rec + 2, make_float4(p.wo.x, p.wo.y, p.wo.z, __uint_as_float(p.series)),
+                   make_float4(p.weight.x, p.weight.y, p.weight.z, __uint_as_float(pixel_index | wf_flags(WF_ACTIVE, true))));
+            wf_st2(cold, make_float4(color.x, color.y, color.z, __uint_as_float(samples_left)),
+                   make_float4(__uint_as_float(chunk), 0.f, 0.f, 0.f));
+            still_active += 1;
+        }
     }
     n_samples = warp_sum(n_samples);
     still_active = __reduce_add_sync(0xFFFFFFFFu, still_active);
@@ -667,6 +574,5 @@ k_wf_regen(const RenderArgs a, WfBuffers wf, unsigned int *active_out, int sorte
         if(still_active) atomicAdd(active_out, still_active);
     }
 }
-#endif
 
 } // namespace ort
