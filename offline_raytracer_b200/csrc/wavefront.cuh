@@ -157,6 +157,15 @@ __device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot,
 #ifndef ORT_SHADE_MIN_BLOCKS
 #define ORT_SHADE_MIN_BLOCKS 8
 #endif
+// measured on B200 (SHADE ms, C3 1080p x 64 spp / C4 4K x 16 spp / 4.4 M-triangle grid; 0 = off 49.0 / 44.1 / 26.8):
+// 148: 48.7 / 43.9 / 26.6, 296: 48.3 / 43.3 / 26.4, 592: 47.4 / 42.0 / 26.2, 888: 47.4 / 42.2 / 26.2, 1184: 47.8 / 42.4 / 26.4,
+// 2368: 49.1 / 43.9 / 27.1, 4736: 51.4 / 46.1 / 28.0; both sectors of the hot block (ORT_SHADE_PREFETCH_BOTH) 48.3 / 42.4 / 26.4 at 592
+#ifndef ORT_SHADE_PREFETCH_BLOCKS
+#define ORT_SHADE_PREFETCH_BLOCKS 592
+#endif
+#ifndef ORT_SHADE_PREFETCH_BOTH
+#define ORT_SHADE_PREFETCH_BOTH 0
+#endif
 // dynamic shared memory: (wide-tree depth + 1) stack rows of 128 uint2 -- sized per scene, so a
 // shallow tree does not pay for ORT_STACK_SIZE rows of occupancy
 #ifndef ORT_EXTEND_FULL_STORE
@@ -437,6 +446,23 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
         float4 *rec = wf.rec + (size_t)WF_REC_QUADS * i;
         float4 ro, rd, swo, sw;
         wf_ld2(rec, ro, rd); wf_ld2(rec + 2, swo, sw);
+#if ORT_SHADE_PREFETCH_BLOCKS
+        // SHADE waits on the record of a slot it only learns from perm[] (ncu: 20 % of its warp samples): ask L2
+        // for the record of the thread ORT_SHADE_PREFETCH_BLOCKS blocks ahead -- about the blocks resident at
+        // once -- while this thread waits for its own
+        if(sorted)
+        {
+            uint32_t jp = j + 128u * ORT_SHADE_PREFETCH_BLOCKS;
+            if(jp < *live)
+            {
+                const float4 *pp = wf.rec + (size_t)WF_REC_QUADS * wf.perm[jp];
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pp));
+#if ORT_SHADE_PREFETCH_BOTH
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pp + 2));
+#endif
+            }
+        }
+#endif
         const uint32_t word = __float_as_uint(sw.w);
         const uint32_t state = wf_state_of(word);
         if(state == WF_ACTIVE)
