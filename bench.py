@@ -313,7 +313,7 @@ def roofline_objects(key, cfg, info, st, per_ray, peaks):
     if not per_ray or "error" in per_ray:
         return None, {}
     rays, kernel_ms = st["rays"], st["device_ms"]
-    wavefront = st["extend_ms"] > 0
+    wavefront = st["extend_ms"] > 0             # the stats pass asks for per-stage events (ORT_WF_TIMING)
     extend_ms = st["extend_ms"] if wavefront else kernel_ms
     n_launch = max(1, st.get("extend_launches", 0)) if wavefront else 1
     rps = rays / (extend_ms * 1e-3)
@@ -458,6 +458,7 @@ class FrameJob:
         """kernel-only time, stage times and ray counts of one step of THIS rank's share (one pool: with two
         overlapping pools the per-stage event times overlap too)"""
         os.environ["ORT_WF_POOLS"] = "1"
+        os.environ["ORT_WF_TIMING"] = "1"           # per-stage events: opt-in, they cost 2-3 % (the timed region runs without)
         try:
             if self.chunked:
                 if not self.my_chunks:
@@ -468,6 +469,7 @@ class FrameJob:
             return st
         finally:
             del os.environ["ORT_WF_POOLS"]
+            del os.environ["ORT_WF_TIMING"]
 
     def checksum(self):
         """64-bit sum of the resolved float image's bit patterns on rank 0: identical for every N"""

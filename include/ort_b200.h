@@ -256,9 +256,11 @@ typedef struct OrtRenderStats
     uint64_t shape_tests;      /* primitive tests        (counters build only, else 0) */
     float    device_ms;        /* CUDA-event time of the kernels of this call */
     uint32_t kernel_launches;  /* kernels launched by this call */
+    /* per-stage times: only when the environment has ORT_WF_TIMING=1 (the event records between the kernels cost
+     * 2-3 % of the frame), else 0 */
     float    extend_ms;        /* wavefront: summed CUDA-event time of the EXTEND launches */
     float    shade_ms;         /* wavefront: ... of the SHADE launches */
-    float    sort_ms;          /* wavefront: ... of the key scan + scatter launches */
+    float    sort_ms;          /* wavefront: ... of the key scatter launches (the scan runs inside EXTEND) */
     uint32_t extend_launches;  /* wavefront: number of EXTEND launches of this call */
 } OrtRenderStats;
 

@@ -163,6 +163,18 @@ __device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot,
 #ifndef ORT_SHADE_PREFETCH_BLOCKS
 #define ORT_SHADE_PREFETCH_BLOCKS 592
 #endif
+// measured on B200 (two-pool frame ms, C3 1080p x 64 spp / C4 4K x 16 spp / 4.4 M-triangle grid): separate k_wf_scan + two
+// memsets per iteration 144.2 / 132.6 / 143.8, fused 142.7 / 130.9 / 143.2
+#ifndef ORT_EXTEND_FUSED_SCAN
+#define ORT_EXTEND_FUSED_SCAN 1
+#endif
+// slots per thread in k_wf_scatter (the kernel is a chain of latencies per block -- keys, shared atomics, one global
+// atomic per key present, the scattered store -- so more independent slots per chain is what speeds it up)
+// measured on B200 (SORT ms per C3 1080p x 64 spp / C4 4K x 16 spp / grid, one pool): 1 slot per thread 12.7 / 12.5 / 7.7,
+// 2: 8.7 / 8.3 / 5.4, 4: 6.9 / 6.6 / 4.4, 6: 6.6 / 6.2 / 4.3, 8: 8.5 / 8.0 / 5.3
+#ifndef ORT_SCATTER_ITEMS
+#define ORT_SCATTER_ITEMS 4
+#endif
 #ifndef ORT_SHADE_PREFETCH_BOTH
 #define ORT_SHADE_PREFETCH_BOTH 0
 #endif
@@ -329,6 +341,42 @@ k_wf_extend(SceneView scene, WfBuffers wf, uint32_t *chunk_counter, unsigned lon
             uint32_t v = ((volatile uint32_t *)sh_hist)[k];
             if(v) atomicAdd(&hist[k], v);
         }
+#if ORT_EXTEND_FUSED_SCAN
+        // The last block of the grid to get here turns the histogram into the cursors of the counting sort
+        // (what k_wf_scan did in a launch of its own) and leaves the histogram, the chunk counter and the
+        // arrival counter zeroed for the next EXTEND of the pool: one launch and two memsets less per iteration.
+        // sort[] = hist[512] | cursor[512] | live | chunk counter | arrival counter (hist == sort).
+        __threadfence();
+        __syncwarp();                      // every lane's histogram atomics are performed before lane 0 announces the block
+        uint32_t last = 0u;
+        if(lane == 0) last = atomicAdd(hist + 2u * WF_KEY_BINS + 2u, 1u) == gridDim.x - 1u ? 1u : 0u;
+        last = __shfl_sync(0xFFFFFFFFu, last, 0);
+        if(last)
+        {
+            __threadfence();
+            uint32_t v[WF_KEY_BINS / 32u], sum = 0u;
+#pragma unroll
+            for(uint32_t k = 0; k < WF_KEY_BINS / 32u; ++k) { v[k] = __ldcg(hist + (WF_KEY_BINS / 32u) * lane + k); sum += v[k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for(uint32_t o = 1; o < 32u; o <<= 1)
+            {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if(lane >= o) incl += u;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for(uint32_t k = 0; k < WF_KEY_BINS / 32u; ++k)
+            {
+                uint32_t bin = (WF_KEY_BINS / 32u) * lane + k;
+                hist[WF_KEY_BINS + bin] = run;                                   // cursor
+                if(bin == WF_KEY_DEAD) hist[2u * WF_KEY_BINS] = run;             // live: everything before the dead bin
+                run += v[k];
+                hist[bin] = 0u;
+            }
+            if(lane == 0) { hist[2u * WF_KEY_BINS + 1u] = 0u; hist[2u * WF_KEY_BINS + 2u] = 0u; }
+        }
+#endif
     }
 }
 
@@ -370,20 +418,31 @@ k_wf_scatter(WfBuffers wf, uint32_t *cursor)
     __shared__ uint32_t cnt[WF_KEY_BINS], base[WF_KEY_BINS];
     for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x) cnt[k] = 0u;
     __syncthreads();
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < wf.capacity;
-    uint32_t key = valid ? wf.key[i] : WF_KEY_BINS;      // padding threads: a key of their own, never counted
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-    uint32_t leader = __ffs(peers) - 1u;
-    uint32_t lane = threadIdx.x & 31u;
-    uint32_t local = 0u;
-    if(lane == leader && valid) local = atomicAdd(&cnt[key], (uint32_t)__popc(peers));
-    local = __shfl_sync(0xFFFFFFFFu, local, leader) + __popc(peers & ((1u << lane) - 1u));
+    const uint32_t lane = threadIdx.x & 31u;
+    // the block takes ORT_SCATTER_ITEMS stripes of 1024 consecutive slots, thread t slot t of each: the 32 slots a warp
+    // ranks at a time stay neighbours in perm[], which is what lets SHADE's warps share record lines (consecutive
+    // slots PER THREAD measured 3 ... 7 % slower in SHADE)
+    const uint32_t i0 = blockIdx.x * (1024u * ORT_SCATTER_ITEMS) + threadIdx.x;
+    uint32_t key[ORT_SCATTER_ITEMS], local[ORT_SCATTER_ITEMS];
+#pragma unroll
+    for(int r = 0; r < ORT_SCATTER_ITEMS; ++r)
+        key[r] = i0 + 1024u * r < wf.capacity ? wf.key[i0 + 1024u * r] : WF_KEY_BINS;      // padding: a key of its own, never counted
+#pragma unroll
+    for(int r = 0; r < ORT_SCATTER_ITEMS; ++r)
+    {
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, key[r]);
+        uint32_t leader = __ffs(peers) - 1u;
+        uint32_t l = 0u;
+        if(lane == leader && key[r] < WF_KEY_BINS) l = atomicAdd(&cnt[key[r]], (uint32_t)__popc(peers));
+        local[r] = __shfl_sync(0xFFFFFFFFu, l, leader) + __popc(peers & ((1u << lane) - 1u));
+    }
     __syncthreads();
     for(uint32_t k = threadIdx.x; k < WF_KEY_BINS; k += blockDim.x)
         if(cnt[k]) base[k] = atomicAdd(&cursor[k], cnt[k]);
     __syncthreads();
-    if(valid) wf.perm[base[key] + local] = i;
+#pragma unroll
+    for(int r = 0; r < ORT_SCATTER_ITEMS; ++r)
+        if(key[r] < WF_KEY_BINS) wf.perm[base[key[r]] + local[r]] = i0 + 1024u * r;
 }
 
 // material + normalised normal of the winning record (ray.cpp:817).  Triangles -- almost all

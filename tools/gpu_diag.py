@@ -49,10 +49,10 @@ if a.scenes:
         hs = ort.HostScene.load(os.path.join(ROOT, "scenes", name + ".scn"), data, w, h)
         sc = ort.Scene(hs.world, hs.root, 0)
         P = ort.default_params(w, h, spp, chunk_spp=16)
-        os.environ["ORT_WF_POOLS"] = "1"
+        os.environ["ORT_WF_POOLS"] = "1"; os.environ["ORT_WF_TIMING"] = "1"
         for _ in range(2):
             img, st = sc.render(hs.camera, P)
-        del os.environ["ORT_WF_POOLS"]
+        del os.environ["ORT_WF_POOLS"]; del os.environ["ORT_WF_TIMING"]
         img, st2 = sc.render(hs.camera, P)
         print(json.dumps({name: {"one_pool": {k: st[k] for k in ("device_ms", "extend_ms", "sort_ms", "shade_ms", "rays", "samples", "shape_tests", "kernel_launches")},
                                  "two_pools_ms": st2["device_ms"], "msamples_s": st2["samples"] / st2["device_ms"] / 1e3}}), flush=True)

@@ -1,6 +1,7 @@
 """Small fixed render used as the target of `ncu --set full` (one k_render_mega launch)."""
 import argparse
 import os
+os.environ.setdefault("ORT_WF_TIMING", "1")
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -14,10 +14,10 @@ for node_cost in ("0.5", "0.75", "1.0", "1.5", "2.5"):
             hs = hosts[name]
             sc = ort.Scene(hs.world, hs.root, 0)
             P = ort.default_params(w, h, spp, chunk_spp=16, kernel=2)
-            os.environ["ORT_WF_POOLS"] = "1"
+            os.environ["ORT_WF_POOLS"] = "1"; os.environ["ORT_WF_TIMING"] = "1"
             sc.render(hs.camera, P)
             _, st = sc.render(hs.camera, P)
-            del os.environ["ORT_WF_POOLS"]
+            del os.environ["ORT_WF_POOLS"]; del os.environ["ORT_WF_TIMING"]
             best = min(sc.render(hs.camera, P)[1]["device_ms"] for _ in range(2))
             row[name[:6]] = {"nodes": sc.info()["bvh_node_count"], "ext": round(st["extend_ms"], 1), "2pool": round(best, 1)}
             sc.close()

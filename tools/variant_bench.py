@@ -23,10 +23,10 @@ for path in libs:
         hs = hosts[tag]
         sc = ort.Scene(hs.world, hs.root, 0, library=L)
         P = ort.default_params(w, h, spp, chunk_spp=16, kernel=2)
-        os.environ["ORT_WF_POOLS"] = "1"
+        os.environ["ORT_WF_POOLS"] = "1"; os.environ["ORT_WF_TIMING"] = "1"
         sc.render(hs.camera, P)
         img, st = sc.render(hs.camera, P)
-        del os.environ["ORT_WF_POOLS"]
+        del os.environ["ORT_WF_POOLS"]; del os.environ["ORT_WF_TIMING"]
         best = 1e30
         for _ in range(2):
             img, st2 = sc.render(hs.camera, P)
