@@ -11,7 +11,9 @@
 //                 global work counter.  A slot therefore always leaves this kernel holding a
 //                 ray (path regeneration), so the wavefront stays full until the work runs out
 //                 and no pool-wide compaction pass is needed while it does.
-//   k_wf_extend   per slot: closest hit of its ray (bvh.h) -> (t, primitive)
+//   k_wf_extend   per slot: closest hit of its ray (bvh.h) -> (t, primitive), the slot's shading key and the
+//                 key histogram; the last block to finish turns the histogram into the sort cursors
+//   k_wf_scatter  counting sort: perm[] = the slots grouped by shading key, for SHADE
 //
 // Why split: the single-kernel form is ~6000 SASS instructions (96 KB); ncu shows its
 // warps starved by instruction-cache misses (icc hit rate 64 %, "no_instruction" the top
