@@ -319,7 +319,7 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
                 *launches += 1;
             }
             if(stage_timing) CUDA_TRY(cudaEventRecord(pl.ev[b][it][2], st));
-            k_wf_shade<<<grid, 128, 0, st>>>(a, pl.wf, act + it, live, sorted);
+            k_wf_shade<<<(cap + ORT_SHADE_THREADS - 1u) / ORT_SHADE_THREADS, ORT_SHADE_THREADS, 0, st>>>(a, pl.wf, act + it, live, sorted);
             if(stage_timing) CUDA_TRY(cudaEventRecord(pl.ev[b][it][3], st));
         }
         *launches += 2 * WF_BATCH;
@@ -356,7 +356,7 @@ int launch_wavefront(OrtScene *s, const RenderArgs &a, cudaStream_t stream, uint
         CUDA_TRY(cudaMemsetAsync(pl.d_sort, 0, (2 * WF_KEY_BINS + 4) * sizeof(uint32_t), pl.stream));
 #endif
         CUDA_TRY(cudaMemsetAsync(pl.d_active, 0, 2 * WF_BATCH * sizeof(unsigned int), pl.stream));
-        k_wf_shade<<<grid, 128, 0, pl.stream>>>(a, pl.wf, pl.d_active, pl.d_sort + 2 * WF_KEY_BINS, 0);
+        k_wf_shade<<<(pl.wf.capacity + ORT_SHADE_THREADS - 1u) / ORT_SHADE_THREADS, ORT_SHADE_THREADS, 0, pl.stream>>>(a, pl.wf, pl.d_active, pl.d_sort + 2 * WF_KEY_BINS, 0);
         *launches += 2;
         rc = enqueue(pl, 0);
         if(rc != ORT_OK) return rc;

@@ -177,6 +177,10 @@ __device__ __forceinline__ void wf_store_hit(const WfBuffers &wf, uint32_t slot,
 #ifndef ORT_SCATTER_ITEMS
 #define ORT_SCATTER_ITEMS 4
 #endif
+// threads per SHADE block = the domain of the regeneration compaction (measured on B200, steady state, profiles/README.md)
+#ifndef ORT_SHADE_THREADS
+#define ORT_SHADE_THREADS 128
+#endif
 #ifndef ORT_SHADE_PREFETCH_BOTH
 #define ORT_SHADE_PREFETCH_BOTH 0
 #endif
@@ -480,10 +484,10 @@ struct WfRegen           // what phase 2 needs to know about a slot whose path e
     uint32_t series, pixel_index, slot, pad0, pad1;
 };
 
-__global__ void __launch_bounds__(128, ORT_SHADE_MIN_BLOCKS)
+__global__ void __launch_bounds__(ORT_SHADE_THREADS, ORT_SHADE_MIN_BLOCKS)
 k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uint32_t *live, int sorted)
 {
-    __shared__ WfRegen sh_regen[128];
+    __shared__ WfRegen sh_regen[ORT_SHADE_THREADS];
     __shared__ uint32_t sh_count;
     if(threadIdx.x == 0) sh_count = 0u;
     __syncthreads();
@@ -513,7 +517,7 @@ k_wf_shade(const RenderArgs a, WfBuffers wf, unsigned int *active_out, const uin
         // once -- while this thread waits for its own
         if(sorted)
         {
-            uint32_t jp = j + 128u * ORT_SHADE_PREFETCH_BLOCKS;
+            uint32_t jp = j + 128u * ORT_SHADE_PREFETCH_BLOCKS;      // in units of 128 slots whatever the block size
             if(jp < *live)
             {
                 const float4 *pp = wf.rec + (size_t)WF_REC_QUADS * wf.perm[jp];
