@@ -418,11 +418,12 @@ int launch_render(OrtScene *s, const OrtCamera *cam, const OrtRenderParams *P, c
         // The two forms give bit-identical images (tests/test_gpu_render.py).  The wavefront needs a few
         // hundred launches to fill and drain its slot pool whatever the job size, so small jobs go to the
         // single-launch megakernel -- measured on B200, testscene.scn, samples in the call:
-        //   2.1 M: 5.0 vs 19.1 ms   8.3 M: 15.6 vs 23.9   29 M: 52.1 vs 41.9   66 M: 115 vs 70.8 (mega vs wavefront)
+        //   2.1 M: 5.0 vs 12.3 ms   8.3 M: 16.5 vs 16.3   14.7 M: 28.6 vs 20.7 (mega vs wavefront, final round-2 kernels;
+        //   before the scan moved into EXTEND and the stage events became opt-in: 16.6, 22.7 and 28.8 ms, threshold 16 M)
         const char *e = getenv("ORT_KERNEL");
         const unsigned long long samples = (unsigned long long)tw * th * (unsigned long long)a.chunk_spp * cp.count;
         if(e && atoi(e) != 0) kernel = atoi(e) == ORT_KERNEL_MEGAKERNEL ? ORT_KERNEL_MEGAKERNEL : ORT_KERNEL_WAVEFRONT;
-        else kernel = samples < 16000000ull ? ORT_KERNEL_MEGAKERNEL : ORT_KERNEL_WAVEFRONT;
+        else kernel = samples < 8000000ull ? ORT_KERNEL_MEGAKERNEL : ORT_KERNEL_WAVEFRONT;
     }
     if(kernel == ORT_KERNEL_WAVEFRONT) return launch_wavefront(s, a, stream, launches);
     if(s->mega_blocks_per_sm == 0)
